@@ -1,0 +1,86 @@
+"""ctypes binding of libditree.so (include/ditree.h).
+
+There is NO fallback: if the shared library is missing or a CUDA device is absent the import of
+the symbols / creation of a context raises.  ``load()`` only dlopens (works on a CPU-only box, used
+by the symbol-export test); creating a :class:`Context` needs a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libditree.so")
+
+c_i64 = C.c_int64
+c_p = C.c_void_p
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", c_p), ("ndim", C.c_int), ("shape", c_i64 * 4)]
+
+
+class ModelCfg(C.Structure):
+    _fields_ = [("action_dim", C.c_int), ("horizon", C.c_int), ("cond_dim", C.c_int), ("emb_dim", C.c_int),
+                ("map_size", C.c_int), ("down_dims", C.c_int * 3), ("max_batch", C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/ditree.h declares
+SIGNATURES = {
+    "dt_ctx_create": (C.c_int, [C.c_int, C.POINTER(c_p)]),
+    "dt_ctx_destroy": (None, [c_p]),
+    "dt_last_error": (C.c_char_p, [c_p]),
+    "dt_version": (C.c_char_p, []),
+    "dt_set_map": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_float, c_p]),
+    "dt_collide_car": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dt_collide_points": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, C.c_double, C.c_double, c_p, c_p]),
+    "dt_collide_ant": (C.c_int, [c_p, c_p, c_i64, c_i64, C.c_double, c_p, c_p]),
+    "dt_local_map": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, C.c_int, C.c_double, C.c_int, c_p, c_p]),
+    "dt_ray_probe": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dt_path_first_obstacle": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dt_lidar_scan": (C.c_int, [c_p, c_p, c_i64, c_p, c_p, c_p, c_p]),
+    "dt_propagate_collide": (C.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_float,
+                                       C.c_float, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, C.c_int, c_p]),
+    "dt_build_cond_car": (C.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_p, C.c_int, c_i64, c_p, C.c_double, c_p, c_p]),
+    "dt_build_cond_ant": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, c_p, C.c_int, c_i64, c_p, C.c_double, c_p, c_p]),
+    "dt_nearest": (C.c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dt_goal_cost_argmin": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_float, C.c_float, c_p, c_p, c_p]),
+    "dt_mppi_reduce": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_int, C.c_float, c_p, c_p, c_p, c_p]),
+    "dt_load_denoiser": (C.c_int, [c_p, C.POINTER(TensorDesc), C.c_int, C.POINTER(ModelCfg), c_p]),
+    "dt_fm_sample": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_int, C.c_double, c_p, c_p, c_p]),
+    "dt_encode_map": (C.c_int, [c_p, c_p, c_i64, c_p, c_p]),
+    "dt_unet_forward": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, c_p, c_p]),
+    "dt_gemm_bf16": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_int, C.c_int, c_p, c_p]),
+    "dt_launch_count": (c_i64, [c_p]),
+    "dt_sync_status": (C.c_int, [c_p, c_p]),
+}
+
+DT_OK, DT_E_CUDA, DT_E_ARG, DT_E_NOMAP, DT_E_NOMODEL, DT_E_INDEX, DT_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+DT_PROP_STOP_ON_COLLISION = 1
+DT_F32, DT_BF16 = 0, 1
+
+_lib = None
+
+
+def load():
+    """dlopen libditree.so and declare every prototype.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ditreeonlineplanner_b200.build` "
+            "(there is no CPU or PyTorch fallback for the DiTree hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class DitreeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libditree error {code}: {msg}")
+        self.code = code

@@ -1,0 +1,194 @@
+// common.cuh -- context, error plumbing and the shared-memory map staging used by every kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ditree.h"
+
+#define DT_MAX_MAP_CELLS 16384  // 128 x 128; the reference's grids are <= 31 x 31
+
+struct dt_denoiser;  // denoiser.cu
+
+struct dt_ctx {
+  int device = 0;
+  std::string err;
+  // occupancy grid staged as bytes (1 = wall), padded to a multiple of 16 bytes for bulk copies
+  uint8_t* d_map = nullptr;
+  int rows = 0, cols = 0;
+  double s_global = 1.0;
+  int map_bytes = 0;  // padded size
+  // device-side status word (DT_E_*), plus small scratch for reductions
+  int* d_status = nullptr;
+  int* h_status = nullptr;  // pinned
+  void* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int64_t launches = 0;
+  int sm_count = 148;
+  dt_denoiser* den = nullptr;
+};
+
+static inline int dt_fail(dt_ctx* ctx, int code, const char* what) {
+  if (ctx) ctx->err = what;
+  return code;
+}
+static inline int dt_fail_cuda(dt_ctx* ctx, cudaError_t e, const char* where) {
+  if (ctx) {
+    ctx->err = std::string(where) + ": " + cudaGetErrorString(e);
+  }
+  return DT_E_CUDA;
+}
+
+#define DT_CUDA(call)                                                      \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) return dt_fail_cuda(ctx, e__, #call);          \
+  } while (0)
+
+#define DT_LAUNCH_CHECK(name)                                              \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) return dt_fail_cuda(ctx, e__, name);           \
+    ctx->launches++;                                                       \
+  } while (0)
+
+int dt_ensure_scratch(dt_ctx* ctx, size_t bytes);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+struct MapView {
+  const uint8_t* g;  // global pointer (padded to map_bytes)
+  int rows, cols, bytes;
+  double s;  // metres per cell
+};
+
+static inline MapView dt_map_view(const dt_ctx* ctx) {
+  MapView m;
+  m.g = ctx->d_map;
+  m.rows = ctx->rows;
+  m.cols = ctx->cols;
+  m.bytes = ctx->map_bytes;
+  m.s = ctx->s_global;
+  return m;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t dt_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Stage the occupancy grid into shared memory with one 1-D bulk TMA copy (cp.async.bulk,
+// SASS UBLKCP) completing on an mbarrier.  Call from every thread of the block; `bar` is a
+// __shared__ uint64_t, `dst` a 16-byte aligned shared buffer of >= m.bytes.
+__device__ __forceinline__ void dt_stage_map(uint8_t* dst, uint64_t* bar, const MapView& m) {
+  const uint32_t bar_a = dt_smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)m.bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dt_smem_u32(dst)),
+        "l"(m.g), "r"((uint32_t)m.bytes), "r"(bar_a)
+        : "memory");
+  }
+  // every thread waits for phase 0 of the barrier
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar_a)
+        : "memory");
+  }
+}
+
+// ---- bit-exact float64 geometry (no FMA contraction: every op is an explicit _rn intrinsic) ----
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ int dt_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// floor() of a double to int with saturation (NumPy's astype(int) is int64; values here are tiny
+// unless the state has diverged, in which case they are out of bounds either way).
+__device__ __forceinline__ int dt_floor_i(double v) {
+  double f = floor(v);
+  if (!(f > -1.0e9)) return -1000000000;  // also catches NaN
+  if (f > 1.0e9) return 1000000000;
+  return (int)f;
+}
+
+// One ball of is_colliding_parallel (common/map_utils.py:221-329) with cell size s, radius r.
+// Returns bit0 = full test result (inside wall | sides | corners), bit1 = out of bounds,
+// bit2 = the diagonal stage would raise IndexError in NumPy (column clipped with the row count),
+// bit3 = already colliding before the diagonal stage (inside wall | sides).
+__device__ __forceinline__ int dt_ball_test(const uint8_t* __restrict__ grid, int R, int C, double s, double r,
+                                            double ax, double ay) {
+  const double cx = xmul(xdiv((double)C, 2.0), s);
+  const double cy = xmul(xdiv((double)R, 2.0), s);
+  const int row = dt_floor_i(xdiv(xsub(cy, ay), s));
+  const int col = dt_floor_i(xdiv(xadd(ax, cx), s));
+  if (row < 0 || row >= R || col < 0 || col >= C) return 2;
+  int hit = grid[row * C + col] == 1;
+  const double mid_x = xsub(xmul(xadd((double)col, 0.5), s), cx);
+  const double mid_y = xsub(cy, xmul(xadd((double)row, 0.5), s));
+  const double h = xdiv(s, 2.0);
+  const double x_lo = xsub(mid_x, h), x_hi = xadd(mid_x, h);
+  const double y_lo = xsub(mid_y, h), y_hi = xadd(mid_y, h);
+  const int cR = dt_clampi(col + 1, 0, C - 1), cL = dt_clampi(col - 1, 0, C - 1);
+  const int rU = dt_clampi(row - 1, 0, R - 1), rD = dt_clampi(row + 1, 0, R - 1);
+  hit |= (xadd(ax, r) > x_hi) & (grid[row * C + cR] == 1);
+  hit |= (xsub(ax, r) < x_lo) & (grid[row * C + cL] == 1);
+  hit |= (xadd(ay, r) > y_hi) & (grid[rU * C + col] == 1);
+  hit |= (xsub(ay, r) < y_lo) & (grid[rD * C + col] == 1);
+  int err = hit ? 8 : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double kx = (k & 1) ? x_lo : x_hi;   // TR, TL, BR, BL
+    const double ky = (k & 2) ? y_lo : y_hi;
+    const int ci = row + ((k & 2) ? 1 : -1);
+    const int cj = col + ((k & 1) ? -1 : 1);
+    const int outside = (ci < 0) | (ci >= R) | (cj < 0) | (cj >= C);
+    const int ci_c = dt_clampi(ci, 0, R - 1);
+    const int cj_c = dt_clampi(cj, 0, R - 1);  // sic: clipped with the ROW count (map_utils.py:326)
+    if (cj_c > C - 1) {                        // NumPy would raise IndexError here
+      err |= 4;
+      continue;
+    }
+    const double d = hypot(xsub(kx, ax), xsub(ky, ay));
+    hit |= outside | ((d < r) & (grid[ci_c * C + cj_c] == 1));
+  }
+  return hit | err;
+}
+
+// is_colliding_car (common/map_utils.py:103-115) on a float32 state up-cast to float64.
+// Returns 0/1, or 1|4 when the reference would raise.
+__device__ __forceinline__ int dt_car_test(const uint8_t* __restrict__ grid, int R, int C, float xf, float yf,
+                                           float thf) {
+  const double th = (double)thf;
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  const double half = xmul(0.15, 0.5);
+  const double ox = xmul(half, cs), oy = xmul(half, sn);
+  const double x = (double)xf, y = (double)yf;
+  const int a = dt_ball_test(grid, R, C, 1.0, 0.1, xadd(x, ox), xadd(y, oy));
+  const int b = dt_ball_test(grid, R, C, 1.0, 0.1, xsub(x, ox), xsub(y, oy));
+  if ((a | b) & 2) return 1;  // a ball out of bounds decides the pair (map_utils.py:255-259 + .any())
+  // the reference returns before the diagonal stage when both balls already collide (:266,:311)
+  const int raises = ((a | b) & 4) && !((a & 8) && (b & 8));
+  return ((a | b) & 1) | (raises ? 4 : 0);
+}
+#endif  // __CUDACC__

@@ -1,0 +1,99 @@
+// ctx.cu -- context lifetime, map upload, status word.
+#include "common.cuh"
+
+void dt_denoiser_free(dt_ctx* ctx);  // denoiser.cu
+
+extern "C" const char* dt_version(void) { return "ditree-b200 0.1 (sm_100a)"; }
+
+extern "C" int dt_ctx_create(int device, dt_ctx** out) {
+  if (!out) return DT_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) return DT_E_CUDA;
+  dt_ctx* ctx = new dt_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DT_E_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DT_E_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    // sm_100a cubins only load on compute capability 10.x parts; fail loudly instead of later
+    fprintf(stderr, "libditree: device %d is sm_%d%d, this library is built for sm_100a only\n", device, prop.major,
+            prop.minor);
+    delete ctx;
+    return DT_E_UNSUPPORTED;
+  }
+  if (cudaMalloc(&ctx->d_status, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_status, sizeof(int)) != cudaSuccess) {
+    delete ctx;
+    return DT_E_CUDA;
+  }
+  *out = ctx;
+  return DT_OK;
+}
+
+extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  dt_denoiser_free(ctx);
+  if (ctx->d_map) cudaFree(ctx->d_map);
+  if (ctx->d_status) cudaFree(ctx->d_status);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  delete ctx;
+}
+
+extern "C" const char* dt_last_error(dt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int64_t dt_launch_count(dt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dt_ensure_scratch(dt_ctx* ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return DT_OK;
+  if (ctx->d_scratch) {
+    DT_CUDA(cudaDeviceSynchronize());
+    DT_CUDA(cudaFree(ctx->d_scratch));
+    ctx->d_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  size_t sz = bytes < (1u << 20) ? (1u << 20) : bytes;
+  DT_CUDA(cudaMalloc(&ctx->d_scratch, sz));
+  ctx->scratch_bytes = sz;
+  return DT_OK;
+}
+
+extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int cols, float s_global, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!grid_host || rows < 1 || cols < 1 || (int64_t)rows * cols > DT_MAX_MAP_CELLS || !(s_global > 0.f))
+    return dt_fail(ctx, DT_E_ARG, "dt_set_map: bad grid (1 <= rows*cols <= 16384, s_global > 0)");
+  DT_CUDA(cudaSetDevice(ctx->device));
+  const int padded = ((rows * cols + 15) / 16) * 16;
+  std::vector<uint8_t> bytes(padded, 0);
+  for (int i = 0; i < rows * cols; ++i) bytes[i] = (grid_host[i] == 1.0f) ? 1 : (grid_host[i] != 0.0f ? 2 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (padded > ctx->map_bytes || !ctx->d_map) {
+    DT_CUDA(cudaStreamSynchronize(st));
+    if (ctx->d_map) DT_CUDA(cudaFree(ctx->d_map));
+    ctx->d_map = nullptr;
+    DT_CUDA(cudaMalloc(&ctx->d_map, padded));
+  }
+  // synchronous: the staging vector dies at return, and the reference's update_maze is synchronous too
+  DT_CUDA(cudaMemcpyAsync(ctx->d_map, bytes.data(), padded, cudaMemcpyHostToDevice, st));
+  DT_CUDA(cudaStreamSynchronize(st));
+  ctx->rows = rows;
+  ctx->cols = cols;
+  ctx->s_global = (double)s_global;
+  ctx->map_bytes = padded;
+  return DT_OK;
+}
+
+extern "C" int dt_sync_status(dt_ctx* ctx, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  DT_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DT_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+  DT_CUDA(cudaStreamSynchronize(st));
+  const int s = *ctx->h_status;
+  if (s == DT_E_INDEX) ctx->err = "index out of range (the reference raises IndexError here)";
+  return s;
+}

@@ -1,0 +1,435 @@
+// geom.cu -- grid geometry kernels: collision tests, robot-centric local maps, obstacle probes,
+// 2-D lidar ray-marching.  All coordinate arithmetic is float64 with explicit round-to-nearest
+// intrinsics (no FMA contraction) so the flags and cell indices are bit-identical to the
+// reference's NumPy float64 code when both are fed the same float32 values.
+#include "common.cuh"
+
+#define GEOM_THREADS 256
+
+// -------------------------------------------------------------------------------------------
+// is_colliding_car  (common/map_utils.py:103-115)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_collide_car(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+              int64_t stride, int64_t B, uint8_t* __restrict__ out, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = dt_car_test(s_map, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
+    if (r & 4) atomicMin(status, DT_E_INDEX);
+    out[i] = (uint8_t)(r & 1);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// is_colliding_parallel  (common/map_utils.py:221-329), two passes for the batch early return
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_collide_points(MapView m, const float* __restrict__ x, const float* __restrict__ y, int64_t stride, int64_t N,
+                 double scale, double r, uint8_t* __restrict__ out, int* __restrict__ any_oob,
+                 int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  int block_oob = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = dt_ball_test(s_map, m.rows, m.cols, scale, r, (double)x[i * stride], (double)y[i * stride]);
+    if (t & 4) atomicMin(status, DT_E_INDEX);
+    out[i] = (uint8_t)(t & 3);
+    block_oob |= (t & 2);
+  }
+  if (__syncthreads_or(block_oob) && threadIdx.x == 0) atomicOr(any_oob, 1);
+}
+
+__global__ void k_select_points(uint8_t* __restrict__ out, int64_t N, const int* __restrict__ any_oob) {
+  const int oob = *any_oob;  // map_utils.py:255-259: if any point is outside, only that mask is returned
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t v = out[i];
+    out[i] = oob ? ((v >> 1) & 1) : (v & 1);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// is_colliding_ant -> is_colliding_maze  (common/map_utils.py:126-218)
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int maze_test(const uint8_t* __restrict__ g, int R, int C, double s, double r, double x,
+                                         double y) {
+  const double cx = xmul(xdiv((double)C, 2.0), s), cy = xmul(xdiv((double)R, 2.0), s);
+  const int row = dt_floor_i(xdiv(xsub(cy, y), s));
+  const int col = dt_floor_i(xdiv(xadd(x, cx), s));
+  if (row < 0 || row >= R || col < 0 || col >= C) return 1;
+  const double mid_x = xsub(xmul(xadd((double)col, 0.5), s), cx);
+  const double mid_y = xsub(cy, xmul(xadd((double)row, 0.5), s));
+  const double h = xdiv(s, 2.0);
+  const double x_lo = xsub(mid_x, h), x_hi = xadd(mid_x, h), y_lo = xsub(mid_y, h), y_hi = xadd(mid_y, h);
+  if (xadd(x, r) > x_hi && (col + 1 >= C || g[row * C + col + 1] == 1)) return 1;
+  if (xsub(x, r) < x_lo && (col - 1 < 0 || g[row * C + col - 1] == 1)) return 1;
+  if (xadd(y, r) > y_hi && (row - 1 < 0 || g[(row - 1) * C + col] == 1)) return 1;
+  if (xsub(y, r) < y_lo && (row + 1 >= R || g[(row + 1) * C + col] == 1)) return 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double kx = (k & 1) ? x_lo : x_hi, ky = (k & 2) ? y_lo : y_hi;
+    const int ci = row + ((k & 2) ? 1 : -1), cj = col + ((k & 1) ? -1 : 1);
+    const double dx = xsub(kx, x), dy = xsub(ky, y);
+    const double d = __dsqrt_rn(xadd(xmul(dx, dx), xmul(dy, dy)));
+    if (d < r && ci >= 0 && ci < R && cj >= 0 && cj < C && g[ci * C + cj] == 1) return 1;
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_collide_ant(MapView m, const float* __restrict__ st, int64_t row_stride, int64_t B, double radius,
+              uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = st + i * row_stride;
+    // slots 3..6 are unpacked as (w, x, y, z) by the matrix builder (common/se3_utils.py:155-164)
+    const double qx = (double)p[4], qy = (double)p[5];
+    const double up = xsub(1.0, xmul(2.0, xadd(xmul(qx, qx), xmul(qy, qy))));
+    int hit = 1;
+    if (!(up < 0.0)) hit = maze_test(s_map, m.rows, m.cols, m.s, radius, (double)p[0], (double)p[1]);
+    out[i] = (uint8_t)hit;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// create_local_map  (common/map_utils.py:391-459): one warp per robot pose
+// -------------------------------------------------------------------------------------------
+struct Axis {
+  double v[32];  // linspace(-L/2 + scale/2, L/2 - scale/2, N), N <= 32
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+            int64_t stride, int64_t B, int N, Axis ax, OutT* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const double cx = xmul(xdiv((double)m.cols, 2.0), m.s), cy = xmul(xdiv((double)m.rows, 2.0), m.s);
+  for (int64_t b = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); b < B;
+       b += (int64_t)gridDim.x * warps_per_block) {
+    double sn = 0.0, cs = 0.0;
+    if (lane == 0) sincos((double)th[b * stride], &sn, &cs);
+    sn = __shfl_sync(0xffffffffu, sn, 0);
+    cs = __shfl_sync(0xffffffffu, cs, 0);
+    const double px = (double)x[b * stride], py = (double)y[b * stride];
+    OutT* o = out + b * (int64_t)(N * N);
+    for (int p = lane; p < N * N; p += 32) {
+      const int i = p / N, j = p - i * N;  // out[i, j] uses ys[i], xs[j]
+      const double xl = ax.v[j], yl = ax.v[i];
+      const double xg = xadd(xsub(xmul(cs, xl), xmul(sn, yl)), px);
+      const double yg = xadd(xadd(xmul(sn, xl), xmul(cs, yl)), py);
+      int yi = dt_floor_i(xdiv(xsub(cy, yg), m.s));
+      int xi = dt_floor_i(xdiv(xadd(xg, cx), m.s));
+      xi = dt_clampi(xi, 0, m.cols - 1);
+      yi = dt_clampi(yi, 0, m.rows - 1);
+      const float occ = (float)s_map[yi * m.cols + xi];
+      if (sizeof(OutT) == 4) {
+        o[p] = (OutT)occ;
+      } else {
+        o[p] = (OutT)(occ * 2.0f - 1.0f);  // sampler's rescale to [-1, 1] (fm_policy.py:152)
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// check_obstacle_ahead  (planners/RRT.py:61-81)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_ray_probe(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+            int64_t stride, int64_t B, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  // the env's cell size is 1 for the car (car_env.py:82)
+  const double cx = xdiv((double)m.cols, 2.0), cy = xdiv((double)m.rows, 2.0);
+  const double step = xdiv(1.5, 29.0);  // linspace(0, 1.5, 30)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const double row = xsub(cy, (double)y[i * stride]);
+    const double col = xadd((double)x[i * stride], cx);
+    double sn, cs;
+    sincos(-(double)th[i * stride], &sn, &cs);
+    int hit = 0;
+    for (int k = 0; k < 30; ++k) {
+      const double t = (k == 29) ? 1.5 : xmul((double)k, step);
+      const double sx = xadd(xmul(t, cs), col), sy = xadd(xmul(t, sn), row);
+      int qx = (int)sx, qy = (int)sy;  // astype('int'): truncation toward zero
+      qx = dt_clampi(qx, 0, m.cols - 1);
+      qy = dt_clampi(qy, 0, m.rows - 1);
+      hit |= (s_map[qy * m.cols + qx] != 0);
+    }
+    out[i] = (uint8_t)hit;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// check_no_obstacles_in_path  (run_scenarios_with_lidar_DiTree.py:158-181): single block
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_path_first_obstacle(MapView m, const float* __restrict__ x, const float* __restrict__ y, int64_t stride, int64_t n,
+                      int32_t* __restrict__ idx_out, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  __shared__ int best;
+  dt_stage_map(s_map, &bar, m);
+  if (threadIdx.x == 0) best = 0x7fffffff;
+  __syncthreads();
+  const double cx = xdiv((double)m.cols, 2.0), cy = xdiv((double)m.rows, 2.0);
+  int mine = 0x7fffffff;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    int r = dt_floor_i(xsub(cy, (double)y[i * stride]));
+    int c = dt_floor_i(xadd((double)x[i * stride], cx));
+    if (r < 0) r += m.rows;  // NumPy negative indices wrap
+    if (c < 0) c += m.cols;
+    if (r < 0 || r >= m.rows || c < 0 || c >= m.cols) {
+      atomicMin(status, DT_E_INDEX);
+      continue;
+    }
+    if (s_map[r * m.cols + c] == 1 && (int)i < mine) mine = (int)i;
+  }
+  atomicMin(&best, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) idx_out[0] = (best == 0x7fffffff) ? -1 : best;
+}
+
+// -------------------------------------------------------------------------------------------
+// Lidar2DSim.scan  (lidar_sim/lidar_2d_sim.py:18-98): one warp per bundle of 32 rays
+// -------------------------------------------------------------------------------------------
+#define LIDAR_RAYS 181
+#define LIDAR_BUNDLES 6  // ceil(181 / 32)
+
+// 2x2 solve with partial pivoting in the operation order of LAPACK's dgesv (which is what
+// numpy.linalg.solve calls): pivot on the larger |a_i0|, scale by the reciprocal, eliminate, back-solve.
+__device__ __forceinline__ bool solve2(double a00, double a01, double a10, double a11, double b0, double b1,
+                                       double* t, double* s) {
+  if (fabs(a10) > fabs(a00)) {
+    double tmp;
+    tmp = a00; a00 = a10; a10 = tmp;
+    tmp = a01; a01 = a11; a11 = tmp;
+    tmp = b0; b0 = b1; b1 = tmp;
+  }
+  if (a00 == 0.0) return false;
+  const double l = xmul(a10, xdiv(1.0, a00));
+  const double u11 = xsub(a11, xmul(l, a01));
+  if (u11 == 0.0) return false;
+  const double y1 = xsub(b1, xmul(l, b0));
+  const double x1 = xdiv(y1, u11);
+  const double x0 = xdiv(xsub(b0, xmul(a01, x1)), a00);
+  *t = x0;
+  *s = x1;
+  return true;
+}
+
+__global__ void __launch_bounds__(LIDAR_BUNDLES * 32)
+k_lidar_scan(MapView m, const float* __restrict__ pose, int64_t B, double* __restrict__ dist_out,
+             double* __restrict__ end_out, uint8_t* __restrict__ visited, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  dt_stage_map(s_map, &bar, m);
+  const int ray = threadIdx.x;  // warp w handles rays 32w .. 32w+31
+  // the reference names maze.shape[0] "width" and uses it as the x extent (lidar_2d_sim.py:51)
+  const double w = (double)m.rows, h = (double)m.cols;
+  const int wi = m.rows, hi = m.cols;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    if (ray >= LIDAR_RAYS) continue;
+    const double x0 = (double)pose[b * 3 + 0], y0 = (double)pose[b * 3 + 1], yaw = (double)pose[b * 3 + 2];
+    const double angle_deg = xadd(-180.0, xmul((double)ray, 2.0));  // arange(-180, 182, 2)
+    const double ang = xmul(xadd(yaw, angle_deg), 0.017453292519943295);  // deg2rad: x * (pi / 180)
+    double rs, rc;
+    sincos(ang, &rs, &rc);
+    // borders in the reference's order: left, right, bottom, top
+    const double bax[4] = {0.0, w, 0.0, 0.0}, bay[4] = {0.0, 0.0, 0.0, h};
+    const double bdx[4] = {0.0, 0.0, w, w}, bdy[4] = {h, h, 0.0, 0.0};
+    bool found = false;
+    double lx = 0.0, ly = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (found) continue;
+      double t, s;
+      if (!solve2(rc, -bdx[k], rs, -bdy[k], xsub(bax[k], x0), xsub(bay[k], y0), &t, &s)) continue;
+      if (t >= 0.0 && 1.0 >= s && s >= 0.0) {
+        lx = xadd(xmul(t, rc), x0);
+        ly = xadd(xmul(t, rs), y0);
+        found = true;
+      }
+    }
+    double hx = lx, hy = ly;
+    if (!found) {
+      // the reference would raise (last_point is None); flag it and report a zero-length ray
+      atomicMin(status, DT_E_INDEX);
+      hx = x0;
+      hy = y0;
+    } else {
+      const double ddx = xsub(lx, x0), ddy = xsub(ly, y0);
+      const double len = __dsqrt_rn(xadd(xmul(ddx, ddx), xmul(ddy, ddy)));
+      const double step = xdiv(0.1, len);
+      // numpy.arange(0, 1, step): ceil((1 - 0) / step) samples t_k = k * step
+      const double cnt_d = ceil(xdiv(1.0, step));
+      const int cnt = cnt_d > 1.0e6 ? 1000000 : (int)cnt_d;
+      uint8_t* vis = visited ? visited + b * (int64_t)(m.rows * m.cols) : nullptr;
+      for (int k = 0; k < cnt; ++k) {
+        const double t = xmul((double)k, step);
+        const double sx = xadd(x0, xmul(t, ddx)), sy = xadd(y0, xmul(t, ddy));
+        int qx = dt_clampi(dt_floor_i(sx), 0, wi - 1);
+        int qy = dt_clampi(dt_floor_i(sy), 0, hi - 1);
+        if (qy >= m.rows || qx >= m.cols) {  // non-square map: the reference indexes out of range
+          atomicMin(status, DT_E_INDEX);
+          break;
+        }
+        if (s_map[qy * m.cols + qx] == 1) {
+          hx = sx;
+          hy = sy;
+          break;
+        }
+        if (vis) vis[qy * m.cols + qx] = 1;
+      }
+    }
+    const double ex = xsub(hx, x0), ey = xsub(hy, y0);
+    double d = __dsqrt_rn(xadd(xmul(ex, ex), xmul(ey, ey)));
+    d = fmin(fmax(d, 0.0), 300.0);  // noise_std = 0, clip to max_range
+    dist_out[b * LIDAR_RAYS + ray] = d;
+    end_out[(b * LIDAR_RAYS + ray) * 2 + 0] = xadd(x0, xmul(d, rc));
+    end_out[(b * LIDAR_RAYS + ray) * 2 + 1] = xadd(y0, xmul(d, rs));
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// host entry points
+// -------------------------------------------------------------------------------------------
+static inline int grid_for(int64_t n, int threads, const dt_ctx* ctx, int per_sm = 8) {
+  int64_t blocks = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;  // grid-stride: a whole number of waves
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+#define NEED_MAP()                                                              \
+  if (!ctx) return DT_E_ARG;                                                    \
+  if (!ctx->d_map) return dt_fail(ctx, DT_E_NOMAP, "dt_set_map has not been called")
+
+extern "C" int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride,
+                              int64_t B, uint8_t* flags_out, void* stream) {
+  NEED_MAP();
+  if (B <= 0) return DT_OK;
+  if (!x || !y || !theta || !flags_out) return dt_fail(ctx, DT_E_ARG, "dt_collide_car: null pointer");
+  MapView m = dt_map_view(ctx);
+  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(
+      m, x, y, theta, stride, B, flags_out, ctx->d_status);
+  DT_LAUNCH_CHECK("k_collide_car");
+  return DT_OK;
+}
+
+extern "C" int dt_collide_points(dt_ctx* ctx, const float* x, const float* y, int64_t stride, int64_t N, double scale,
+                                 double r, uint8_t* flags_out, void* stream) {
+  NEED_MAP();
+  if (N <= 0) return DT_OK;
+  if (!x || !y || !flags_out) return dt_fail(ctx, DT_E_ARG, "dt_collide_points: null pointer");
+  MapView m = dt_map_view(ctx);
+  int rc = dt_ensure_scratch(ctx, 256);
+  if (rc) return rc;
+  int* any_oob = (int*)ctx->d_scratch;
+  cudaStream_t st = (cudaStream_t)stream;
+  DT_CUDA(cudaMemsetAsync(any_oob, 0, sizeof(int), st));
+  k_collide_points<<<grid_for(N, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes, st>>>(m, x, y, stride, N, scale, r,
+                                                                                  flags_out, any_oob, ctx->d_status);
+  DT_LAUNCH_CHECK("k_collide_points");
+  k_select_points<<<grid_for(N, GEOM_THREADS, ctx), GEOM_THREADS, 0, st>>>(flags_out, N, any_oob);
+  DT_LAUNCH_CHECK("k_select_points");
+  return DT_OK;
+}
+
+extern "C" int dt_collide_ant(dt_ctx* ctx, const float* states, int64_t row_stride, int64_t B, double radius,
+                              uint8_t* flags_out, void* stream) {
+  NEED_MAP();
+  if (B <= 0) return DT_OK;
+  if (!states || !flags_out || row_stride < 7) return dt_fail(ctx, DT_E_ARG, "dt_collide_ant: bad argument");
+  MapView m = dt_map_view(ctx);
+  k_collide_ant<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(
+      m, states, row_stride, B, radius, flags_out);
+  DT_LAUNCH_CHECK("k_collide_ant");
+  return DT_OK;
+}
+
+extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
+                            int N, double scale, int out_dtype, void* out, void* stream) {
+  NEED_MAP();
+  if (B <= 0) return DT_OK;
+  if (!x || !y || !theta || !out) return dt_fail(ctx, DT_E_ARG, "dt_local_map: null pointer");
+  if (N < 2 || N > 32) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_local_map: N must be in [2, 32]");
+  // numpy.linspace(start, stop, N): arange(N) * step + start, last element forced to stop
+  Axis ax;
+  {
+    volatile double L = (double)N * scale;
+    volatile double start = -L / 2 + scale / 2, stop = L / 2 - scale / 2;
+    volatile double step = (stop - start) / (double)(N - 1);
+    for (int i = 0; i < N; ++i) {
+      volatile double prod = (double)i * step;
+      ax.v[i] = prod + start;
+    }
+    ax.v[N - 1] = stop;
+    for (int i = N; i < 32; ++i) ax.v[i] = 0.0;
+  }
+  MapView m = dt_map_view(ctx);
+  const int warps = GEOM_THREADS / 32;
+  int64_t blocks = (B + warps - 1) / warps;
+  if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == DT_F32) {
+    k_local_map<float><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, (float*)out);
+  } else if (out_dtype == DT_BF16) {
+    k_local_map<__nv_bfloat16><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax,
+                                                                          (__nv_bfloat16*)out);
+  } else {
+    return dt_fail(ctx, DT_E_ARG, "dt_local_map: unknown out_dtype");
+  }
+  DT_LAUNCH_CHECK("k_local_map");
+  return DT_OK;
+}
+
+extern "C" int dt_ray_probe(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
+                            uint8_t* flags_out, void* stream) {
+  NEED_MAP();
+  if (B <= 0) return DT_OK;
+  if (!x || !y || !theta || !flags_out) return dt_fail(ctx, DT_E_ARG, "dt_ray_probe: null pointer");
+  MapView m = dt_map_view(ctx);
+  k_ray_probe<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(m, x, y, theta, stride,
+                                                                                               B, flags_out);
+  DT_LAUNCH_CHECK("k_ray_probe");
+  return DT_OK;
+}
+
+extern "C" int dt_path_first_obstacle(dt_ctx* ctx, const float* x, const float* y, int64_t stride, int64_t n,
+                                      int32_t* idx_out, void* stream) {
+  NEED_MAP();
+  if (!idx_out) return dt_fail(ctx, DT_E_ARG, "dt_path_first_obstacle: null pointer");
+  if (n > 0 && (!x || !y)) return dt_fail(ctx, DT_E_ARG, "dt_path_first_obstacle: null pointer");
+  MapView m = dt_map_view(ctx);
+  k_path_first_obstacle<<<1, GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(m, x, y, stride, n, idx_out,
+                                                                           ctx->d_status);
+  DT_LAUNCH_CHECK("k_path_first_obstacle");
+  return DT_OK;
+}
+
+extern "C" int dt_lidar_scan(dt_ctx* ctx, const float* pose, int64_t B, double* dist_out, double* end_out,
+                             uint8_t* visited_out, void* stream) {
+  NEED_MAP();
+  if (B <= 0) return DT_OK;
+  if (!pose || !dist_out || !end_out) return dt_fail(ctx, DT_E_ARG, "dt_lidar_scan: null pointer");
+  MapView m = dt_map_view(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (visited_out) DT_CUDA(cudaMemsetAsync(visited_out, 0, (size_t)B * m.rows * m.cols, st));
+  int64_t blocks = B;
+  if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+  k_lidar_scan<<<(int)blocks, LIDAR_BUNDLES * 32, m.bytes, st>>>(m, pose, B, dist_out, end_out, visited_out,
+                                                                 ctx->d_status);
+  DT_LAUNCH_CHECK("k_lidar_scan");
+  return DT_OK;
+}

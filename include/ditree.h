@@ -1,0 +1,190 @@
+/* ditree.h -- C ABI of libditree.so: the B200 (sm_100a) tree-expansion hot path of DiTree.
+ *
+ * Drop-in boundary.  Every entry point replaces one reference function (cited per declaration as
+ * file:line of the upstream repository).  The reference is pure Python, so the binding a
+ * maintainer adds is a ctypes stub (INTEGRATION.md shows it for each call).
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers owned by the caller unless the name ends in _host.
+ *  - Functions only enqueue work on `stream` (a cudaStream_t passed as void*) and return an int
+ *    status: 0 = OK, <0 = DT_E_*.  They never throw.  dt_last_error(ctx) returns a message.
+ *  - One dt_ctx per device owns the staged occupancy grid, packed denoiser weights and scratch.
+ *    A ctx is re-entrant across ctxs but not thread-safe within one (like the reference, which
+ *    is single-threaded and synchronous).
+ *  - Strided arrays: element (candidate b, component d[, step s]) lives at
+ *        base[b*cand_stride + s*step_stride + d*comp_stride]      (strides in elements)
+ *    so the same kernels take the reference's array-of-structs layouts ((B,D), (B,S,A)) and the
+ *    coalesced struct-of-arrays layouts ((D,B), (S,A,B)) the device pipeline uses.
+ */
+#ifndef DITREE_H
+#define DITREE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dt_ctx dt_ctx;
+
+enum {
+  DT_OK = 0,
+  DT_E_CUDA = -1,       /* a CUDA runtime/driver call failed (message has the CUDA error) */
+  DT_E_ARG = -2,        /* invalid argument (NULL pointer, size out of range, ...) */
+  DT_E_NOMAP = -3,      /* dt_set_map has not been called */
+  DT_E_NOMODEL = -4,    /* dt_load_denoiser has not been called */
+  DT_E_INDEX = -5,      /* the reference would raise IndexError (tall map, map_utils.py:326) */
+  DT_E_UNSUPPORTED = -6 /* shape not supported by the sm_100a kernels */
+};
+
+enum { DT_PROP_STOP_ON_COLLISION = 1 }; /* flags of dt_propagate_collide */
+enum { DT_F32 = 0, DT_BF16 = 1 };
+
+/* ---- context ------------------------------------------------------------------------------ */
+int dt_ctx_create(int device, dt_ctx** out);
+void dt_ctx_destroy(dt_ctx* ctx);
+const char* dt_last_error(dt_ctx* ctx);
+const char* dt_version(void);
+
+/* Occupancy grid upload.  Replaces RRT_Planner.update_maze / BasePlanner.maze
+ * (planners/RRT.py:57-59, planners/base_planner.py:117).  grid_host: rows*cols floats, row-major,
+ * cell value 1 = wall.  s_global = metres per cell (1 car, 4 ant). Synchronous on `stream`. */
+int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int cols, float s_global, void* stream);
+
+/* ---- geometry ----------------------------------------------------------------------------- */
+/* is_colliding_car (common/map_utils.py:103-115 -> is_colliding_parallel :221-329) for B states;
+ * x/y/theta strided by `stride` elements.  flags_out[b] in {0,1}.  Bit-exact vs float64 NumPy
+ * when fed the same float32 values. */
+int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
+                   uint8_t* flags_out, void* stream);
+
+/* is_colliding_parallel itself (common/map_utils.py:221-329) for N points with cell size `scale`
+ * and ball radius r, INCLUDING the whole-batch early return with only the out-of-bounds mask
+ * (:255-259).  Returns DT_E_INDEX through dt_sync_status when the reference would raise. */
+int dt_collide_points(dt_ctx* ctx, const float* x, const float* y, int64_t stride, int64_t N, double scale, double r,
+                      uint8_t* flags_out, void* stream);
+
+/* is_colliding_ant (common/map_utils.py:126-136 -> is_colliding_maze :139-218); states: B rows of
+ * >= 7 floats (x, y, z, q0..q3) with row stride `row_stride`; uses the ctx map scale. */
+int dt_collide_ant(dt_ctx* ctx, const float* states, int64_t row_stride, int64_t B, double radius, uint8_t* flags_out,
+                   void* stream);
+
+/* create_local_map (common/map_utils.py:391-459): B robot-centric N x N crops.
+ * out_dtype DT_F32: out is (B,N,N) float32 in {0,1} (the reference's array);
+ * out_dtype DT_BF16: out is (B,N,N) bf16 holding 2*m-1 (the sampler's rescale, fm_policy.py:152),
+ * the encoder's input format. */
+int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B, int N,
+                 double scale, int out_dtype, void* out, void* stream);
+
+/* check_obstacle_ahead (planners/RRT.py:61-81). */
+int dt_ray_probe(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
+                 uint8_t* flags_out, void* stream);
+
+/* check_no_obstacles_in_path (run_scenarios_with_lidar_DiTree.py:158-181): index of the first of
+ * n path points (x,y strided) whose cell == 1 in the ctx map, else -1, written to idx_out[0]. */
+int dt_path_first_obstacle(dt_ctx* ctx, const float* x, const float* y, int64_t stride, int64_t n, int32_t* idx_out,
+                           void* stream);
+
+/* Lidar2DSim.scan (lidar_sim/lidar_2d_sim.py:18-98, noise_std = 0) for B poses in GRID coordinates
+ * (x = col, y = row, yaw): 181 rays each.  dist_out (B,181) f64, end_out (B,181,2) f64,
+ * visited_out nullable (B, rows*cols) u8 mask of cells the rays crossed before their hit. */
+int dt_lidar_scan(dt_ctx* ctx, const float* pose, int64_t B, double* dist_out, double* end_out, uint8_t* visited_out,
+                  void* stream);
+
+/* ---- dynamics ----------------------------------------------------------------------------- */
+/* Fused BasePlanner.propagate_action_sequence_env (planners/base_planner.py:257-320) over
+ * CarEnv.step/_update_state/_check_done (car_env.py:240-282,341-396) + is_colliding_car, one
+ * thread per candidate, all S Euler steps in registers.
+ *   state0 / state_out : 6 components, strided (s_cand, s_comp)
+ *   actions            : strided (a_cand, a_step, a_comp), 2 components
+ *   traj_out (nullable): strided (t_cand, t_step, t_comp), 6 components; rows after the edge ends
+ *                        are zero (the reference leaves them zero and strips them, RRT.py:196-199)
+ *   first_coll[b] = first step whose state collides, -1 none;  done_step[b] = step at which the goal
+ *   disc (0.5 m, car_env.py:349) was entered, -1 none.  With DT_PROP_STOP_ON_COLLISION the edge ends
+ *   at the first collision (reference behaviour: the planner drops such edges, RRT.py:179-184). */
+int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_cand, int64_t s_comp, const float* actions,
+                         int64_t a_cand, int64_t a_step, int64_t a_comp, int64_t B, int S, float goal_x, float goal_y,
+                         float* traj_out, int64_t t_cand, int64_t t_step, int64_t t_comp, float* state_out,
+                         int32_t* first_coll, int32_t* done_step, int flags, void* stream);
+
+/* ---- sampler conditioning (policies/fm_policy.py:53-143) ------------------------------------ */
+/* car: cond (B,7) f32 = [v_n, D_n, delta_n, a0_n, a1_n, tanh(R(-yaw)(goal-p)/map_size)].
+ * state strided (s_cand, s_comp); prev_action (B,2) rows or NULL (zeros, un-normalised);
+ * goal: goal_stride = 0 -> one (2,) goal for all, 2 -> (B,2).  norm: 16 doubles on the HOST:
+ * obs_mean[6], obs_std[6], act_mean[2], act_std[2]. */
+int dt_build_cond_car(dt_ctx* ctx, const float* state, int64_t s_cand, int64_t s_comp, const float* prev_action,
+                      const float* goal, int goal_stride, int64_t B, const double* norm_host, double map_size,
+                      float* cond_out, void* stream);
+
+/* ant: obs_seq (B,h,29) f32 rows (x, y, 27 dims), h <= obs_history; cond (B, obs_history*29+8+2).
+ * norm_host: obs_mean[27], obs_std[27], act_mean[8], act_std[8]. */
+int dt_build_cond_ant(dt_ctx* ctx, const float* obs_seq, int h, int obs_history, const float* prev_action,
+                      const float* goal, int goal_stride, int64_t B, const double* norm_host, double map_size,
+                      float* cond_out, void* stream);
+
+/* ---- reductions ----------------------------------------------------------------------------- */
+/* RRT_Planner.nearest_node[_batch] (planners/RRT.py:49-55): 1-NN in (x,y) over n nodes for Q
+ * queries, squared distance in float64, lowest index on ties. */
+int dt_nearest(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, const float* qx, const float* qy,
+               int64_t q_stride, int64_t Q, int32_t* idx_out, void* stream);
+
+/* Final node selection (planners/RRT.py:233-237): argmin_i ||p_i - goal|| + 1e4*ahead[i] (ahead
+ * nullable), float64, first index on ties; idx_out[0]. */
+int dt_goal_cost_argmin(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, float goal_x, float goal_y,
+                        const uint8_t* ahead, int32_t* idx_out, void* stream);
+
+/* MPPI cost reduction (call sites run_scenarios_with_lidar_MPPI.py:339-341,422; PARITY UNPINNED:
+ * the reference's MPPI module is not in its repository).  w = softmax(-(c - min c)/lambda);
+ * u[t,a] += sum_k w_k noise[k,t,a]; argmin_out[0] = argmin c.  cost (K) f32, noise (K,TA) f32,
+ * u_inout (TA) f32, weights_out nullable (K) f32. */
+int dt_mppi_reduce(dt_ctx* ctx, const float* cost, const float* noise, int64_t K, int TA, float lambda, float* u_inout,
+                   int32_t* argmin_out, float* weights_out, void* stream);
+
+/* ---- denoiser (local_map_encoder.py:78-122, conditional_unet1d.py:268-347, fm_policy.py:152-203) */
+typedef struct {
+  const char* name;   /* reference state_dict key, e.g. "unet.mid_modules.0.blocks.0.block.0.weight" */
+  const float* data;  /* HOST pointer, float32, contiguous */
+  int ndim;
+  int64_t shape[4];
+} dt_tensor_desc;
+
+typedef struct {
+  int action_dim;   /* A: 2 car, 8 ant */
+  int horizon;      /* T = pred_horizon: 64 car, 16 ant */
+  int cond_dim;     /* G: 7 car, 97 ant */
+  int emb_dim;      /* local-map embedding: 400 */
+  int map_size;     /* N: 20 car, 16 ant */
+  int down_dims[3]; /* e.g. 512,1024,2048 */
+  int max_batch;    /* scratch is sized for this many candidates */
+} dt_model_cfg;
+
+/* Pack a reference `noise_pred_net_state_dict` (run_scenarios.py:175-176) into bf16 GEMM operands. */
+int dt_load_denoiser(dt_ctx* ctx, const dt_tensor_desc* tensors, int n_tensors, const dt_model_cfg* cfg, void* stream);
+
+/* DiffusionSampler.forward's flow-matching loop (fm_policy.py:183-203): K Euler steps of the
+ * denoiser from `noise`.  noise (B,T,A) f32, cond (B,G) f32, local_map (B,N,N) bf16 holding 2m-1
+ * (dt_local_map DT_BF16).  actions_out (B,T,A) f32 = a*act_std + act_mean (norm_host: act_mean[A],
+ * act_std[A]); pass norm_host = NULL for the normalised sample. */
+int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, const void* local_map, int64_t B, int K,
+                 double exp_scale, const double* norm_host, float* actions_out, void* stream);
+
+/* Pieces of the denoiser, exported for the parity tests: encoder only -> emb_out (B,emb) f32;
+ * one U-Net evaluation at `timestep` (already scaled by 20) -> vel_out (B,T,A) f32. */
+int dt_encode_map(dt_ctx* ctx, const void* local_map, int64_t B, float* emb_out, void* stream);
+int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* emb, const float* cond, int64_t B, float timestep,
+                    float* vel_out, void* stream);
+
+/* Test hook for the tcgen05 GEMM core: C[M,N] (f32) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16). */
+int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C, void* stream);
+
+/* Number of kernels this library launched since the ctx was created (bench.py's gpu_launches). */
+int64_t dt_launch_count(dt_ctx* ctx);
+
+/* Asynchronous device-side status raised by earlier launches (e.g. DT_E_INDEX); synchronises
+ * `stream`, returns and clears it. */
+int dt_sync_status(dt_ctx* ctx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DITREE_H */

@@ -1,0 +1,54 @@
+"""CPU-side checks of the boundary: the C-ABI library is built, loads, and exports every symbol
+include/ditree.h declares (no compute call is made without a GPU)."""
+import os
+import re
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ditreeonlineplanner_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from ditreeonlineplanner_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "ditree.h")).read()
+    declared = set(re.findall(r"\b(dt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"dt_ctx", "dt_tensor_desc", "dt_model_cfg"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_version_and_null_ctx(lib):
+    assert b"sm_100a" in lib.dt_version()
+    assert lib.dt_last_error(None) == b"null context"
+    assert lib.dt_launch_count(None) == 0
+
+
+def test_no_cpu_fallback():
+    """The product package never imports the oracle and refuses to run without CUDA."""
+    import torch
+    pkg = os.path.join(REPO, "ditreeonlineplanner_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+    if not torch.cuda.is_available():
+        from ditreeonlineplanner_b200 import Context
+        with pytest.raises(RuntimeError):
+            Context(0)
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    from ditreeonlineplanner_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

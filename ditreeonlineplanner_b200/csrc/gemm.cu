@@ -1,6 +1,640 @@
-// gemm.cu -- placeholder, replaced by the tcgen05 GEMM core.
-#include "common.cuh"
+// gemm.cu -- the tcgen05 implicit-GEMM core of the denoiser.
+//
+//   D[M = B*T rows, N = Cout] = sum over K-segments  A_seg[M, 64*nblk] * W[N, Kseg]^T      (bf16 in, fp32 acc)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: per 64-channel K block one 4-D tensor-map load of the activation
+//               tile (channel, phase, time, sample) -- conv taps are time offsets of the box, the
+//               zero padding is TMA's out-of-bounds fill, channel concat is a second tensor map --
+//               and one 2-D load of the weight tile; 128-byte swizzle; mbarrier complete_tx.
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (64/128/256), K=16,
+//               operands straight from shared memory through UMMA descriptors, accumulator in
+//               TMEM (two BN-column buffers so the epilogue of tile i overlaps the MMAs of i+1).
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (one row per thread), then either
+//               bias (+residual, +ReLU)  or  bias -> GroupNorm -> Mish -> FiLM (+residual);
+//               GroupNorm statistics are tile-local because a tile holds whole samples (M tile =
+//               128/T samples x T rows) and whole groups (BN is a multiple of the group width).
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+#define BM 128
+#define BK 64
+#define GEMM_THREADS 192
+#define SPIN_LIMIT (1u << 27)
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();  // a protocol bug must fault, not hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row atoms of
+// 1024 B (SBO = 64 x 16 B), LBO unused for swizzled K-major (canonical value 1), version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)
+__device__ __forceinline__ float mish_f(float x) {
+  if (x > 20.0f) return x;
+  const float e = __expf(x);
+  const float n = e * (e + 2.0f);
+  return x * __fdividef(n, n + 2.0f);
+}
+
+template <int NG>
+__device__ __forceinline__ float pick(const float (&a)[NG], int i) {
+  float r = a[0];
+#pragma unroll
+  for (int k = 1; k < NG; ++k) r = (i == k) ? a[k] : r;
+  return r;
+}
+
+struct GemmDev {
+  int num_m_tiles, num_n_tiles, nseg, nkb_total;
+  int T, rows_t, nb, tiles_per_sample;
+  GemmSeg seg[GEMM_MAX_SEG];
+  long long B;
+  int N;
+  // epilogue
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* film;
+  long long film_ld;
+  const float* film_t;
+  const __nv_bfloat16* resid;
+  long long ld_res;
+  int relu;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  long long ldc, out_b_stride, out_t_stride, out_off;
+};
+
+template <int BN>
+struct SmemPlan {
+  static constexpr int kStageA = BM * BK * 2;
+  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
+  static constexpr int kRedFloats = 4 * 8 * 2 * 2;             // [parity][warp][group][sum,sq]
+  static constexpr int kBytes = kStages * kStage + (kParamFloats + kRedFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+template <int BN, int EPI, int GW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+            const __grid_constant__ CUtensorMap mapW, const GemmDev g) {
+  using P = SmemPlan<BN>;
+  constexpr int NG = (EPI == EPI_GN_MISH) ? BN / GW : 1;
+  static_assert(NG <= 8, "at most 8 GroupNorm groups per N tile");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = dt_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  float* s_par = reinterpret_cast<float*>(base_ptr + P::kStages * P::kStage);
+  float* s_red = s_par + P::kParamFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + P::kRedFloats);
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  const uint32_t bar_full = dt_smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * P::kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * P::kStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * P::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 128, 256 or 512: powers of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < P::kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dt_smem_u32(s_tmem)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int total_tiles = g.num_m_tiles * g.num_n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / g.num_n_tiles, n_tile = tile - m_tile * g.num_n_tiles;
+      int b_base, t_base;
+      if (g.tiles_per_sample > 0) {
+        b_base = m_tile / g.tiles_per_sample;
+        t_base = (m_tile - b_base * g.tiles_per_sample) * BM;
+      } else {
+        b_base = m_tile * g.nb;
+        t_base = 0;
+      }
+      int kw = 0;
+      for (int s = 0; s < g.nseg; ++s) {
+        const GemmSeg sg = g.seg[s];
+        const CUtensorMap* mA = sg.src ? &mapA1 : &mapA0;
+        for (int blk = 0; blk < sg.nblk; ++blk, ++kw) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (lane == 0) {
+            const uint32_t sa = base + stage * P::kStage;
+            mbar_expect_tx(bar_full + 8 * stage, P::kStage);
+            tma_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
+            tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN);
+          }
+          __syncwarp();
+          if (++stage == P::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < g.nkb_total; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + stage * P::kStage;
+          const uint64_t da = umma_desc(sa), db = umma_desc(sa + P::kStageA);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte address field
+            tc_mma(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (kb == g.nkb_total - 1) tc_commit(bar_tfull + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == P::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;           // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;    // row inside the M tile
+    const int et = threadIdx.x - 64;  // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / g.num_n_tiles, n_tile = tile - m_tile * g.num_n_tiles;
+      const int n0 = n_tile * BN;
+      long long b;
+      int t;
+      if (g.tiles_per_sample > 0) {
+        b = m_tile / g.tiles_per_sample;
+        t = (m_tile - (int)b * g.tiles_per_sample) * BM + row;
+      } else {
+        b = (long long)m_tile * g.nb + row / g.T;
+        t = row % g.T;
+      }
+      const bool valid = (b < g.B) && (t < g.T);
+      // stage the per-column parameters of this N tile
+      for (int i = et; i < BN; i += 128) {
+        s_par[i] = g.bias ? g.bias[n0 + i] : 0.f;
+        if (EPI == EPI_GN_MISH) {
+          s_par[BN + i] = g.gamma[n0 + i];
+          s_par[2 * BN + i] = g.beta[n0 + i];
+          s_par[3 * BN + i] = g.film_t ? g.film_t[n0 + i] : 0.f;
+          s_par[4 * BN + i] = g.film_t ? g.film_t[g.N + n0 + i] : 0.f;
+        }
+      }
+      epi_bar_sync();
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off;
+
+      float mean[NG], rstd[NG];
+      if (EPI == EPI_GN_MISH) {
+        float gs[NG], gq[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) gs[i] = gq[i] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]) + s_par[c0 + j];
+            gs[(c0 + j) / GW] += v;
+            gq[(c0 + j) / GW] += v * v;
+          }
+        }
+        // reduce over the rows of this sample: lanes first, then warps when a sample spans several
+        const int span = g.T < 32 ? g.T : 32;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          for (int off = 1; off < span; off <<= 1) {
+            gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], off);
+            gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
+          }
+        }
+        if (g.T > 32) {
+          float* red = s_red + (it & 1) * (4 * 8 * 2);
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+              red[(q * 8 + i) * 2 + 0] = gs[i];
+              red[(q * 8 + i) * 2 + 1] = gq[i];
+            }
+          }
+          epi_bar_sync();
+          const int wps = (g.T >= 128 ? 128 : g.T) / 32;  // warps per sample inside this tile
+          const int first = (q / wps) * wps;
+#pragma unroll
+          for (int i = 0; i < NG; ++i) {
+            float a = 0.f, c = 0.f;
+            for (int w = first; w < first + wps; ++w) {
+              a += red[(w * 8 + i) * 2 + 0];
+              c += red[(w * 8 + i) * 2 + 1];
+            }
+            gs[i] = a;
+            gq[i] = c;
+          }
+        }
+        const float inv_n = 1.0f / (float)((g.T > 128 ? 128 : g.T) * GW);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          mean[i] = gs[i] * inv_n;
+          const float var = fmaxf(gq[i] * inv_n - mean[i] * mean[i], 0.f);
+          rstd[i] = rsqrtf(var + 1e-5f);
+        }
+      }
+
+      // second pass: normalise / activate / modulate and store
+      const float* film_row = (EPI == EPI_GN_MISH && g.film && valid) ? g.film + b * g.film_ld + n0 : nullptr;
+      const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + n0 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        float y[32];
+        if (EPI == EPI_GN_MISH) {
+          // groups touched by this 32-column chunk: one when GW >= 32, else 32 / GW
+          constexpr int GPC = (GW >= 32) ? 1 : 32 / GW;
+          float cm[GPC], cr[GPC];
+#pragma unroll
+          for (int u = 0; u < GPC; ++u) {
+            cm[u] = pick<NG>(mean, c0 / GW + u);
+            cr[u] = pick<NG>(rstd, c0 / GW + u);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int u = (GW >= 32) ? 0 : j / GW;
+            const float v = __uint_as_float(r[j]) + s_par[c0 + j];
+            y[j] = mish_f((v - cm[u]) * cr[u] * s_par[BN + c0 + j] + s_par[2 * BN + c0 + j]);
+          }
+          if (film_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + c0 + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(film_row + g.N + c0 + j));
+              y[j + 0] = y[j + 0] * (sc.x + s_par[3 * BN + c0 + j + 0]) + (sh.x + s_par[4 * BN + c0 + j + 0]);
+              y[j + 1] = y[j + 1] * (sc.y + s_par[3 * BN + c0 + j + 1]) + (sh.y + s_par[4 * BN + c0 + j + 1]);
+              y[j + 2] = y[j + 2] * (sc.z + s_par[3 * BN + c0 + j + 2]) + (sh.z + s_par[4 * BN + c0 + j + 2]);
+              y[j + 3] = y[j + 3] * (sc.w + s_par[3 * BN + c0 + j + 3]) + (sh.w + s_par[4 * BN + c0 + j + 3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + s_par[c0 + j];
+        }
+        if (res_row) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 pk = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + j));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __bfloat1622float2(h2[u]);
+              y[j + 2 * u] += f.x;
+              y[j + 2 * u + 1] += f.y;
+            }
+          }
+        }
+        if (EPI == EPI_PLAIN && g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
+        if (valid) {
+          if (g.out_bf16) {
+            __nv_bfloat16* o = g.out_bf16 + out_row * g.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(y[j + 2 * u], y[j + 2 * u + 1]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+          if (g.out_f32) {
+            float* o = g.out_f32 + out_row * g.ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+        }
+      }
+      // release the accumulator to the MMA warp
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps and dispatch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_act_map(dt_ctx* ctx, CUtensorMap* m, const ActSrc& a, int64_t B, int rows_t, int nb) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return dt_fail(ctx, DT_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if (a.C % 8 != 0 || a.T_in % a.P != 0) return dt_fail(ctx, DT_E_UNSUPPORTED, "activation shape not TMA-addressable");
+  cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.P, (cuuint64_t)(a.T_in / a.P), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.P * a.C * 2, (cuuint64_t)a.T_in * a.C * 2};
+  cuuint32_t box[4] = {BK, 1, (cuuint32_t)rows_t, (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act C=%d T=%d P=%d B=%lld) failed: %d", a.C, a.T_in, a.P,
+             (long long)B, (int)r);
+    return dt_fail(ctx, DT_E_CUDA, buf);
+  }
+  return DT_OK;
+}
+
+static int make_w_map(dt_ctx* ctx, CUtensorMap* m, const __nv_bfloat16* w, int N, int64_t Ktot, int bn) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return dt_fail(ctx, DT_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(w N=%d K=%lld) failed: %d", N, (long long)Ktot, (int)r);
+    return dt_fail(ctx, DT_E_CUDA, buf);
+  }
+  return DT_OK;
+}
+
+template <int BN, int EPI, int GW>
+static int launch_gemm(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                       const GemmDev& d, cudaStream_t st) {
+  using P = SmemPlan<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DT_CUDA(cudaFuncSetAttribute(k_conv_gemm<BN, EPI, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    attr_set = true;
+  }
+  const int total = d.num_m_tiles * d.num_n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;  // persistent: one CTA per SM
+  k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
+  DT_LAUNCH_CHECK("k_conv_gemm");
+  return DT_OK;
+}
+
+int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
+  if (g.B <= 0) return DT_OK;
+  if (g.nseg < 1 || g.nseg > GEMM_MAX_SEG || !g.w || !g.a[0].ptr || g.N % 64 != 0)
+    return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad problem description");
+  // tile geometry: a tile holds whole samples (T <= 128) or a 128-row slice of one sample
+  int T = g.T, rows_t, nb, tps;
+  if (T >= BM) {
+    if (T % BM != 0 && g.epi == EPI_GN_MISH) return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm epilogue needs T <= 128");
+    rows_t = BM;
+    nb = 1;
+    tps = (T + BM - 1) / BM;
+  } else {
+    if (BM % T != 0) return dt_fail(ctx, DT_E_UNSUPPORTED, "rows per sample must divide 128");
+    rows_t = T;
+    nb = BM / T;
+    tps = 0;
+  }
+  if (g.epi == EPI_GN_MISH && T > BM) return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm epilogue needs T <= 128");
+  int bn = 256;
+  if (g.epi == EPI_GN_MISH) {
+    const int gw = g.group_width;
+    if (gw == 8) bn = 64;
+    else if (gw == 16) bn = 128;
+    else if (gw == 32 || gw == 64 || gw == 128 || gw == 256) bn = 256;
+    else return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm group width must be 8..256 (power of two)");
+    if (g.N % bn != 0) return dt_fail(ctx, DT_E_UNSUPPORTED, "Cout must be a multiple of the N tile");
+    if (!g.gamma || !g.beta) return dt_fail(ctx, DT_E_ARG, "GroupNorm epilogue needs gamma/beta");
+  } else {
+    bn = (g.N % 256 == 0) ? 256 : ((g.N % 128 == 0) ? 128 : 64);
+  }
+  GemmDev d;
+  memset(&d, 0, sizeof d);
+  int64_t ktot = 0;
+  for (int s = 0; s < g.nseg; ++s) {
+    d.seg[s] = g.seg[s];
+    ktot += (int64_t)g.seg[s].nblk * BK;
+    if (g.seg[s].src < 0 || g.seg[s].src >= g.n_src) return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad segment source");
+  }
+  d.nseg = g.nseg;
+  d.nkb_total = (int)(ktot / BK);
+  d.T = T;
+  d.rows_t = rows_t;
+  d.nb = nb;
+  d.tiles_per_sample = tps;
+  d.num_m_tiles = tps > 0 ? (int)(g.B * tps) : (int)((g.B + nb - 1) / nb);
+  d.num_n_tiles = g.N / bn;
+  d.B = g.B;
+  d.N = g.N;
+  d.bias = g.bias; d.gamma = g.gamma; d.beta = g.beta;
+  d.film = g.film; d.film_ld = g.film_ld; d.film_t = g.film_t;
+  d.resid = g.resid; d.ld_res = g.ld_res; d.relu = g.relu;
+  d.out_bf16 = g.out_bf16; d.out_f32 = g.out_f32;
+  d.ldc = g.ldc; d.out_b_stride = g.out_b_stride; d.out_t_stride = g.out_t_stride; d.out_off = g.out_off;
+  if (!d.out_bf16 && !d.out_f32) return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: no output");
+
+  CUtensorMap mA0, mA1, mW;
+  int rc = make_act_map(ctx, &mA0, g.a[0], g.B, rows_t, nb);
+  if (rc) return rc;
+  if (g.n_src > 1) {
+    rc = make_act_map(ctx, &mA1, g.a[1], g.B, rows_t, nb);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0;
+  }
+  rc = make_w_map(ctx, &mW, g.w, g.N, ktot, bn);
+  if (rc) return rc;
+
+  if (g.epi == EPI_PLAIN) {
+    if (bn == 256) return launch_gemm<256, EPI_PLAIN, 256>(ctx, mA0, mA1, mW, d, st);
+    if (bn == 128) return launch_gemm<128, EPI_PLAIN, 128>(ctx, mA0, mA1, mW, d, st);
+    return launch_gemm<64, EPI_PLAIN, 64>(ctx, mA0, mA1, mW, d, st);
+  }
+  switch (g.group_width) {
+    case 8: return launch_gemm<64, EPI_GN_MISH, 8>(ctx, mA0, mA1, mW, d, st);
+    case 16: return launch_gemm<128, EPI_GN_MISH, 16>(ctx, mA0, mA1, mW, d, st);
+    case 32: return launch_gemm<256, EPI_GN_MISH, 32>(ctx, mA0, mA1, mW, d, st);
+    case 64: return launch_gemm<256, EPI_GN_MISH, 64>(ctx, mA0, mA1, mW, d, st);
+    case 128: return launch_gemm<256, EPI_GN_MISH, 128>(ctx, mA0, mA1, mW, d, st);
+    case 256: return launch_gemm<256, EPI_GN_MISH, 256>(ctx, mA0, mA1, mW, d, st);
+  }
+  return dt_fail(ctx, DT_E_UNSUPPORTED, "unsupported GroupNorm group width");
+}
+
+// Test hook: C[M,N] f32 = A[M,K] bf16 row-major * W[N,K]^T bf16 (K, N multiples of 64).
 extern "C" int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C,
                             void* stream) {
-  return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_gemm_bf16: not built yet");
+  if (!ctx) return DT_E_ARG;
+  if (!A || !W || !C || M <= 0 || N % 64 != 0 || K % 64 != 0) return dt_fail(ctx, DT_E_ARG, "dt_gemm_bf16: bad argument");
+  ConvGemm g;
+  g.a[0].ptr = (const __nv_bfloat16*)A;
+  g.a[0].C = K;
+  g.a[0].T_in = (int)((M + BM - 1) / BM) * BM >= M ? (int)M : (int)M;
+  g.a[0].P = 1;
+  g.n_src = 1;
+  g.w = (const __nv_bfloat16*)W;
+  g.N = N;
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{0, 0, 0, K / BK};
+  g.B = 1;
+  g.T = (int)M;   // one "sample" of M rows, tiled in 128-row slices
+  g.epi = EPI_PLAIN;
+  g.out_f32 = C;
+  g.ldc = N;
+  g.out_b_stride = 0;
+  g.out_t_stride = 1;
+  return dt_conv_gemm(ctx, g, (cudaStream_t)stream);
 }

@@ -240,7 +240,7 @@ def gen_propagate():
     cases.append((start.copy(), np.tile(np.array([[2.0, 0.1]]), (8, 1))))
     wall_xy = env0.cell_rowcol_to_xy(np.array([17, 1]))  # free cell next to the left border wall
     cases.append((np.array([wall_xy[0], wall_xy[1], np.pi, 3.5, 1.0, 0.0]), np.tile(np.array([[5.0, 0.0]]), (8, 1))))
-    cases.append((np.array([goal_xy[0] - 0.62, goal_xy[1], 0.0, 3.0, 0.5, 0.0]), np.tile(np.array([[0.0, 0.0]]), (8, 1))))
+    cases.append((np.array([goal_xy[0] - 0.63, goal_xy[1], 0.0, 3.0, 0.5, 0.0]), np.tile(np.array([[0.0, 0.0]]), (8, 1))))
     for _ in range(40):
         cell = None
         while cell is None:

@@ -542,8 +542,13 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
     rows_t = BM;
     nb = 1;
     tps = (T + BM - 1) / BM;
+  } else if (BM % T != 0) {
+    // odd row count: one (partially filled) tile per sample, rows >= T are masked
+    if (g.epi == EPI_GN_MISH) return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm epilogue needs T to divide 128");
+    rows_t = BM;
+    nb = 1;
+    tps = 1;
   } else {
-    if (BM % T != 0) return dt_fail(ctx, DT_E_UNSUPPORTED, "rows per sample must divide 128");
     rows_t = T;
     nb = BM / T;
     tps = 0;

@@ -30,6 +30,10 @@ struct dt_ctx {
   int64_t launches = 0;
   int sm_count = 148;
   dt_denoiser* den = nullptr;
+  // optional per-launch event timing of the GEMM kernels (dt_profile_begin / dt_profile_end)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
+  size_t prof_used = 0;
 };
 
 static inline int dt_fail(dt_ctx* ctx, int code, const char* what) {

@@ -41,10 +41,44 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   delete ctx;
 }
 
 extern "C" const char* dt_last_error(dt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int dt_profile_begin(dt_ctx* ctx) {
+  if (!ctx) return DT_E_ARG;
+  ctx->prof_on = true;
+  ctx->prof_used = 0;
+  return DT_OK;
+}
+
+extern "C" int dt_profile_end(dt_ctx* ctx, double* gemm_ms_out, int64_t* gemm_launches_out) {
+  if (!ctx) return DT_E_ARG;
+  ctx->prof_on = false;
+  DT_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    float t = 0.f;
+    DT_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    ms += t;
+  }
+  if (gemm_ms_out) *gemm_ms_out = ms;
+  if (gemm_launches_out) *gemm_launches_out = (int64_t)(ctx->prof_used / 2);
+  ctx->prof_used = 0;
+  return DT_OK;
+}
+
+// next event of the profiling pool (created on demand)
+cudaEvent_t dt_prof_event(dt_ctx* ctx) {
+  if (ctx->prof_used == ctx->prof_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    ctx->prof_events.push_back(e);
+  }
+  return ctx->prof_events[ctx->prof_used++];
+}
 
 extern "C" int64_t dt_launch_count(dt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

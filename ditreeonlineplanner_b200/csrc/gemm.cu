@@ -461,6 +461,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps and dispatch
 // ------------------------------------------------------------------------------------------
+cudaEvent_t dt_prof_event(dt_ctx* ctx);  // ctx.cu
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -526,6 +528,16 @@ static int launch_gemm(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1
   }
   const int total = d.num_m_tiles * d.num_n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;  // persistent: one CTA per SM
+  if (ctx->prof_on) {
+    cudaEvent_t e0 = dt_prof_event(ctx), e1 = dt_prof_event(ctx);
+    if (e0 && e1) {
+      cudaEventRecord(e0, st);
+      k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
+      cudaEventRecord(e1, st);
+      DT_LAUNCH_CHECK("k_conv_gemm");
+      return DT_OK;
+    }
+  }
   k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
   DT_LAUNCH_CHECK("k_conv_gemm");
   return DT_OK;

@@ -67,6 +67,15 @@ class Context:
             raise IndexError(self.lib.dt_last_error(self.h).decode())
         self._check(rc)
 
+    def profile_begin(self):
+        self._check(self.lib.dt_profile_begin(self.h))
+
+    def profile_end(self):
+        """-> (summed GEMM kernel milliseconds, GEMM launches) since profile_begin."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self.lib.dt_profile_end(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def launches(self):
         return int(self.lib.dt_launch_count(self.h))

@@ -177,6 +177,12 @@ int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* emb, const fl
 /* Test hook for the tcgen05 GEMM core: C[M,N] (f32) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16). */
 int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C, void* stream);
 
+/* Per-launch device timing of the tensor-core GEMM kernels (bench.py's roofline): between begin and
+ * end every k_conv_gemm launch is bracketed by CUDA events on its own stream.  dt_profile_end
+ * synchronises the device and returns the summed kernel time (ms) and the number of launches. */
+int dt_profile_begin(dt_ctx* ctx);
+int dt_profile_end(dt_ctx* ctx, double* gemm_ms_out, int64_t* gemm_launches_out);
+
 /* Number of kernels this library launched since the ctx was created (bench.py's gpu_launches). */
 int64_t dt_launch_count(dt_ctx* ctx);
 

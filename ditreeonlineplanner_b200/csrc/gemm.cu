@@ -10,7 +10,8 @@
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN (64/128/256), K=16,
 //               operands straight from shared memory through UMMA descriptors, accumulator in
 //               TMEM (two BN-column buffers so the epilogue of tile i overlaps the MMAs of i+1).
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (one row per thread), then either
+//   warps 2..9  epilogue: tcgen05.ld the accumulator (one row per thread, two warps per lane
+//               quarter splitting the columns), then either
 //               bias (+residual, +ReLU)  or  bias -> GroupNorm -> Mish -> FiLM (+residual);
 //               GroupNorm statistics are tile-local because a tile holds whole samples (M tile =
 //               128/T samples x T rows) and whole groups (BN is a multiple of the group width).
@@ -20,7 +21,7 @@
 
 #define BM 128
 #define BK 64
-#define GEMM_THREADS 192
+#define GEMM_THREADS 320
 #define SPIN_LIMIT (1u << 27)
 
 // ------------------------------------------------------------------------------------------
@@ -89,7 +90,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row atoms of
 // 1024 B (SBO = 64 x 16 B), LBO unused for swizzled K-major (canonical value 1), version 1.
@@ -147,7 +148,7 @@ struct SmemPlan {
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
-  static constexpr int kRedFloats = 4 * 8 * 2 * 2;             // [parity][warp][group][sum,sq]
+  static constexpr int kRedFloats = 2 * 8 * 8 * 8 * 2;         // [parity][warp][segment][group][sum,sq]
   static constexpr int kBytes = kStages * kStage + (kParamFloats + kRedFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -182,7 +183,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -274,10 +275,16 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;           // TMEM lane quarter this warp may touch
-    const int row = q * 32 + lane;    // row inside the M tile
-    const int et = threadIdx.x - 64;  // 0..127
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): the pair splits
+    // the BN accumulator columns in halves, so each SM sub-partition has two epilogue warps to overlap
+    // TMEM loads, the Mish MUFU chain and the global FiLM / residual loads.
+    constexpr int HALF = BN / 2;
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int half = (warp - 2) >> 2;       // which half of the columns
+    const int ew = warp - 2;                // 0..7
+    const int row = q * 32 + lane;          // row inside the M tile
+    const int et = threadIdx.x - 64;        // 0..255
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -294,8 +301,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         t = row % g.T;
       }
       const bool valid = (b < g.B) && (t < g.T);
-      // stage the per-column parameters of this N tile
-      for (int i = et; i < BN; i += 128) {
+      // stage the per-column parameters of this N tile (previous tile's readers are past their last use:
+      // they have all arrived on the barrier below in the previous iteration before anyone gets here twice)
+      epi_bar_sync();
+      for (int i = et; i < BN; i += 256) {
         s_par[i] = g.bias ? g.bias[n0 + i] : 0.f;
         if (EPI == EPI_GN_MISH) {
           s_par[BN + i] = g.gamma[n0 + i];
@@ -307,26 +316,42 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       epi_bar_sync();
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
       const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off;
+      const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
 
       float mean[NG], rstd[NG];
       if (EPI == EPI_GN_MISH) {
         float gs[NG], gq[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) gs[i] = gq[i] = 0.f;
+        // pass 1: per-row partial sums of (acc + bias) and its square for the groups in this half
+        if (half == 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
+          for (int c0 = 0; c0 < HALF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]) + s_par[c0 + j];
-            gs[(c0 + j) / GW] += v;
-            gq[(c0 + j) / GW] += v * v;
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) + sp[c0 + j];
+              gs[(c0 + j) / GW] += v;
+              gq[(c0 + j) / GW] += v * v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HALF; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]) + sp[c0 + j];
+              gs[(HALF + c0 + j) / GW] += v;
+              gq[(HALF + c0 + j) / GW] += v * v;
+            }
           }
         }
-        // reduce over the rows of this sample: lanes first, then warps when a sample spans several
+        // reduce over the rows of this sample held by this warp (segments of min(T,32) lanes) ...
         const int span = g.T < 32 ? g.T : 32;
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
@@ -335,43 +360,44 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
           }
         }
-        if (g.T > 32) {
-          float* red = s_red + (it & 1) * (4 * 8 * 2);
-          if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < NG; ++i) {
-              red[(q * 8 + i) * 2 + 0] = gs[i];
-              red[(q * 8 + i) * 2 + 1] = gq[i];
-            }
-          }
-          epi_bar_sync();
-          const int wps = (g.T >= 128 ? 128 : g.T) / 32;  // warps per sample inside this tile
-          const int first = (q / wps) * wps;
+        // ... then across warps through shared memory: the partner half always, other quarters when T > 32
+        float* red = s_red + (it & 1) * (8 * 8 * 8 * 2);
+        const int seg = lane / span;
+        if ((lane % span) == 0) {
 #pragma unroll
           for (int i = 0; i < NG; ++i) {
-            float a = 0.f, c = 0.f;
-            for (int w = first; w < first + wps; ++w) {
-              a += red[(w * 8 + i) * 2 + 0];
-              c += red[(w * 8 + i) * 2 + 1];
-            }
-            gs[i] = a;
-            gq[i] = c;
+            red[((ew * 8 + seg) * 8 + i) * 2 + 0] = gs[i];
+            red[((ew * 8 + seg) * 8 + i) * 2 + 1] = gq[i];
           }
         }
-        const float inv_n = 1.0f / (float)((g.T > 128 ? 128 : g.T) * GW);
+        epi_bar_sync();
+        const int rows_s = g.T > BM ? BM : g.T;       // rows of one sample inside this tile
+        const int wps = rows_s > 32 ? rows_s / 32 : 1;  // lane quarters per sample
+        const int q0 = (q / wps) * wps;
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
-          mean[i] = gs[i] * inv_n;
-          const float var = fmaxf(gq[i] * inv_n - mean[i] * mean[i], 0.f);
+          float a = 0.f, c = 0.f;
+          for (int qq = q0; qq < q0 + wps; ++qq) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int w2 = ((qq + 2) & 3) + 4 * hh;  // ew of the warp with lane quarter qq, half hh
+              a += red[((w2 * 8 + seg) * 8 + i) * 2 + 0];
+              c += red[((w2 * 8 + seg) * 8 + i) * 2 + 1];
+            }
+          }
+          const float inv_n = 1.0f / (float)(rows_s * GW);
+          mean[i] = a * inv_n;
+          const float var = fmaxf(c * inv_n - mean[i] * mean[i], 0.f);
           rstd[i] = rsqrtf(var + 1e-5f);
         }
       }
 
-      // second pass: normalise / activate / modulate and store
-      const float* film_row = (EPI == EPI_GN_MISH && g.film && valid) ? g.film + b * g.film_ld + n0 : nullptr;
-      const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + n0 : nullptr;
+      // pass 2: normalise / activate / modulate and store this warp's half of the columns
+      const int nh = n0 + half * HALF;
+      const float* film_row = (EPI == EPI_GN_MISH && g.film && valid) ? g.film + b * g.film_ld + nh : nullptr;
+      const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + nh : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < HALF; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         float y[32];
@@ -381,29 +407,39 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           float cm[GPC], cr[GPC];
 #pragma unroll
           for (int u = 0; u < GPC; ++u) {
-            cm[u] = pick<NG>(mean, c0 / GW + u);
-            cr[u] = pick<NG>(rstd, c0 / GW + u);
+            cm[u] = pick<NG>(mean, (half * HALF + c0) / GW + u);
+            cr[u] = pick<NG>(rstd, (half * HALF + c0) / GW + u);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int u = (GW >= 32) ? 0 : j / GW;
-            const float v = __uint_as_float(r[j]) + s_par[c0 + j];
-            y[j] = mish_f((v - cm[u]) * cr[u] * s_par[BN + c0 + j] + s_par[2 * BN + c0 + j]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
+            const float4 ga = *reinterpret_cast<const float4*>(sp + BN + c0 + j);
+            const float4 be = *reinterpret_cast<const float4*>(sp + 2 * BN + c0 + j);
+            const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, gam[4] = {ga.x, ga.y, ga.z, ga.w},
+                        bet[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int u = (GW >= 32) ? 0 : (j + e) / GW;
+              const float v = __uint_as_float(r[j + e]) + bia[e];
+              y[j + e] = mish_f((v - cm[u]) * cr[u] * gam[e] + bet[e]);
+            }
           }
           if (film_row) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + c0 + j));
               const float4 sh = __ldg(reinterpret_cast<const float4*>(film_row + g.N + c0 + j));
-              y[j + 0] = y[j + 0] * (sc.x + s_par[3 * BN + c0 + j + 0]) + (sh.x + s_par[4 * BN + c0 + j + 0]);
-              y[j + 1] = y[j + 1] * (sc.y + s_par[3 * BN + c0 + j + 1]) + (sh.y + s_par[4 * BN + c0 + j + 1]);
-              y[j + 2] = y[j + 2] * (sc.z + s_par[3 * BN + c0 + j + 2]) + (sh.z + s_par[4 * BN + c0 + j + 2]);
-              y[j + 3] = y[j + 3] * (sc.w + s_par[3 * BN + c0 + j + 3]) + (sh.w + s_par[4 * BN + c0 + j + 3]);
+              const float4 ts = *reinterpret_cast<const float4*>(sp + 3 * BN + c0 + j);
+              const float4 tb = *reinterpret_cast<const float4*>(sp + 4 * BN + c0 + j);
+              y[j + 0] = y[j + 0] * (sc.x + ts.x) + (sh.x + tb.x);
+              y[j + 1] = y[j + 1] * (sc.y + ts.y) + (sh.y + tb.y);
+              y[j + 2] = y[j + 2] * (sc.z + ts.z) + (sh.z + tb.z);
+              y[j + 3] = y[j + 3] * (sc.w + ts.w) + (sh.w + tb.w);
             }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + s_par[c0 + j];
+          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + sp[c0 + j];
         }
         if (res_row) {
 #pragma unroll
@@ -424,7 +460,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         }
         if (valid) {
           if (g.out_bf16) {
-            __nv_bfloat16* o = g.out_bf16 + out_row * g.ldc + n0 + c0;
+            __nv_bfloat16* o = g.out_bf16 + out_row * g.ldc + nh + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 pk;
@@ -435,7 +471,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             }
           }
           if (g.out_f32) {
-            float* o = g.out_f32 + out_row * g.ldc + n0 + c0;
+            float* o = g.out_f32 + out_row * g.ldc + nh + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }

@@ -53,6 +53,7 @@ SIGNATURES = {
     "dt_gemm_bf16": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_int, C.c_int, c_p, c_p]),
     "dt_profile_begin": (C.c_int, [c_p]),
     "dt_profile_end": (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64)]),
+    "dt_profile_csv": (C.c_int, [c_p, C.c_char_p]),
     "dt_launch_count": (c_i64, [c_p]),
     "dt_sync_status": (C.c_int, [c_p, c_p]),
 }

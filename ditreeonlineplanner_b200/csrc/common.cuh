@@ -34,6 +34,8 @@ struct dt_ctx {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
   size_t prof_used = 0;
+  struct ProfRec { int bn, epi, gw; long long M; int N; long long K; float ms; };
+  std::vector<ProfRec> prof_recs;
 };
 
 static inline int dt_fail(dt_ctx* ctx, int code, const char* what) {

@@ -51,6 +51,7 @@ extern "C" int dt_profile_begin(dt_ctx* ctx) {
   if (!ctx) return DT_E_ARG;
   ctx->prof_on = true;
   ctx->prof_used = 0;
+  ctx->prof_recs.clear();
   return DT_OK;
 }
 
@@ -63,10 +64,26 @@ extern "C" int dt_profile_end(dt_ctx* ctx, double* gemm_ms_out, int64_t* gemm_la
     float t = 0.f;
     DT_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
     ms += t;
+    if (i / 2 < ctx->prof_recs.size()) ctx->prof_recs[i / 2].ms = t;
   }
   if (gemm_ms_out) *gemm_ms_out = ms;
   if (gemm_launches_out) *gemm_launches_out = (int64_t)(ctx->prof_used / 2);
   ctx->prof_used = 0;
+  return DT_OK;
+}
+
+extern "C" int dt_profile_csv(dt_ctx* ctx, const char* path) {
+  if (!ctx || !path) return DT_E_ARG;
+  FILE* f = fopen(path, "w");
+  if (!f) return dt_fail(ctx, DT_E_ARG, "dt_profile_csv: cannot open file");
+  fprintf(f, "idx,BN,epi,gw,M,N,K,ms,tflops\n");
+  for (size_t i = 0; i < ctx->prof_recs.size(); ++i) {
+    const dt_ctx::ProfRec& r = ctx->prof_recs[i];
+    const double fl = 2.0 * (double)r.M * r.N * (double)r.K;
+    fprintf(f, "%zu,%d,%d,%d,%lld,%d,%lld,%.5f,%.1f\n", i, r.bn, r.epi, r.gw, r.M, r.N, r.K, r.ms,
+            r.ms > 0 ? fl / (r.ms * 1e-3) / 1e12 : 0.0);
+  }
+  fclose(f);
   return DT_OK;
 }
 

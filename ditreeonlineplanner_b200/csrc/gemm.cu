@@ -567,6 +567,8 @@ static int launch_gemm(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1
   if (ctx->prof_on) {
     cudaEvent_t e0 = dt_prof_event(ctx), e1 = dt_prof_event(ctx);
     if (e0 && e1) {
+      dt_ctx::ProfRec rec{BN, EPI, GW, (long long)d.B * d.T, d.N, (long long)d.nkb_total * BK, 0.f};
+      ctx->prof_recs.push_back(rec);
       cudaEventRecord(e0, st);
       k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
       cudaEventRecord(e1, st);

@@ -1,0 +1,315 @@
+"""Drop-in mirror of the reference's ``planners/RRT.py::RRT_Planner`` (constructor :19-31, reset
+:33-47, nearest_node[_batch] :49-55, update_maze :57-59, check_obstacle_ahead :61-81, plan :113-257)
+whose expansion runs on the B200:
+
+* ``batch_size = 1`` (default) follows the reference loop statement by statement -- same RNG
+  consumption order, one node inserted per iteration -- with the nearest-neighbour
+  query, local map, sampler, propagation and collision checks executed by the device kernels.
+* ``batch_size = B > 1`` expands B sampled states per round in one batched device pass per chunk
+  (``TreeExpander``): every candidate edge is computed exactly as in the B = 1 loop, but the B
+  samples of a round see the tree as it was at the start of the round (documented deviation).
+
+The wall-clock budget is kept (``time.time()``); ``iteration_cap`` (kwarg, optional) bounds the
+number of sampler calls for deterministic runs.
+"""
+from __future__ import annotations
+
+import random
+import time
+
+import numpy as np
+import torch
+
+from ..common.map_utils import _ctx_for
+from .base_planner import BasePlanner, Node
+
+
+class _DeviceTree:
+    """SoA mirror of the node positions in HBM (x[], y[]) for the nearest-neighbour kernel; replaces
+    the KD-tree the reference rebuilds from scratch after every insertion (RRT.py:207)."""
+
+    def __init__(self, device, capacity=1024):
+        self.device = device
+        self.cap = capacity
+        self.x = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.y = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.n = 0
+
+    def clear(self):
+        self.n = 0
+
+    def append(self, xy_rows):
+        xy = torch.as_tensor(np.asarray(xy_rows, dtype=np.float32).reshape(-1, 2), device=self.device)
+        k = xy.shape[0]
+        if self.n + k > self.cap:
+            while self.n + k > self.cap:
+                self.cap *= 2
+            nx = torch.empty(self.cap, dtype=torch.float32, device=self.device)
+            ny = torch.empty(self.cap, dtype=torch.float32, device=self.device)
+            nx[:self.n], ny[:self.n] = self.x[:self.n], self.y[:self.n]
+            self.x, self.y = nx, ny
+        self.x[self.n:self.n + k] = xy[:, 0]
+        self.y[self.n:self.n + k] = xy[:, 1]
+        self.n += k
+
+
+class RRT_Planner(BasePlanner):
+    def __init__(self, start_state, goal_state, environment, sampler, **kwargs):
+        super().__init__(start_state, goal_state, environment, sampler, **kwargs)
+        self.kd_tree_dim = 2
+        self.goal_sample_rate = 0.15
+        self.goal_conditioning_bias = kwargs.get("goal_conditioning_bias", 0.85)
+        self.prop_duration_schedule = kwargs.get("prop_duration", [64])
+        self.offline_time_budget = kwargs.get("offline_time_budget", 60)
+        self.plan_count = 0
+        self.init_main_path = None
+        self.run_type = kwargs.get("run_type", 0)
+        if self.run_type >= 2:
+            raise NotImplementedError("probability-map sampling (run_type >= 2) is a later row of the scope table")
+        self.env.run_type = self.run_type
+        self.batch_size = int(kwargs.get("batch_size", 1))
+        self.iteration_cap = kwargs.get("iteration_cap", None)
+        self._ctx = _ctx_for(self.maze, 1.0)
+        self._tree = _DeviceTree(self._ctx.device)
+        self._tree.append(np.asarray(start_state[:2]))
+        self.start_node.index = 0
+
+    # ---- bookkeeping ------------------------------------------------------------------------
+    def reset(self, start_state: np.ndarray = None, goal_state: np.ndarray = None, reset_main_path: bool = False):
+        if reset_main_path:
+            self.init_main_path = None
+        if start_state is not None:
+            self.start_node = Node(start_state)
+            self.goal_state = goal_state
+            self.options["reset_cell"] = self.env.cell_xy_to_rowcol(start_state[:2])
+            self.options["reset_deg"] = np.rad2deg(start_state[2])
+            self.options["goal_cell"] = self.env.cell_xy_to_rowcol(goal_state[:2])
+        self.node_list = [self.start_node]
+        self.start_node.index = 0
+        self.failed_node_list = []
+        self._tree.clear()
+        self._tree.append(np.asarray(self.start_node.state[:2]))
+        self.results = {"iterations": 0, "time": 0, "path": None, "actions": None, "number_of_nodes": 0}
+        self.env.reset(options=self.options)
+
+    def _insert(self, node):
+        node.index = len(self.node_list)
+        self.node_list.append(node)
+        self._tree.append(np.asarray(node.state[:2]))
+
+    def nearest_node(self, sample):
+        idx = self._ctx.nearest(self._tree.x[:self._tree.n], self._tree.y[:self._tree.n],
+                                torch.as_tensor(np.asarray(sample, dtype=np.float32)[:, :2]))
+        return self.node_list[int(idx[0])]
+
+    def nearest_node_batch(self, samples):
+        idx = self._ctx.nearest(self._tree.x[:self._tree.n], self._tree.y[:self._tree.n],
+                                torch.as_tensor(np.asarray(samples, dtype=np.float32)[:, :2]))
+        return [self.node_list[i] for i in idx.cpu().tolist()]
+
+    def update_maze(self, new_maze):
+        self.maze = new_maze
+        self.env.maze_map = new_maze
+        self._ctx = _ctx_for(np.float32(new_maze), 1.0)
+
+    def check_obstacle_ahead(self, state):
+        st = np.asarray(state, dtype=np.float32)[None, :3]
+        self._ctx = _ctx_for(self.maze, 1.0)
+        return bool(self._ctx.ray_probe(torch.as_tensor(st))[0])
+
+    def extract_path_after_obstacle(self):
+        """RRT.py:83-111: the part of the previous main path beyond the first scanned obstacle."""
+        path = self.init_main_path[:, :2].copy()
+        cur = self.env.state[:2]
+        near = int(np.argmin(np.linalg.norm(cur - self.init_main_path[:, :2], axis=1)))
+        path = path[near:, :]
+        rc = np.array([self.env.cell_xy_to_rowcol(p).astype("int") for p in path])
+        hit = -1
+        for i, p in enumerate(rc):
+            if self.maze[p[0], p[1]] == 1:
+                hit = i
+                break
+        cp = rc[hit]
+        while self.maze[cp[0], cp[1]] == 1 and hit < len(rc):
+            cp = rc[hit]
+            hit += 1
+        return path[hit:]
+
+    # ---- planning ---------------------------------------------------------------------------
+    def _sample_state(self, remain_init_path):
+        if remain_init_path is not None:
+            node_idx = np.random.choice(np.arange(len(remain_init_path)))
+            return self.random_node_sample() if random.random() < 0.4 else remain_init_path[node_idx][np.newaxis]
+        return self.random_node_sample()
+
+    def _pick_goal(self, sample_node):
+        if self.run_type == 0:
+            return sample_node[0, :2] if random.random() > self.goal_conditioning_bias else self.goal_state[:2]
+        return sample_node[0, :2]
+
+    def _local_map(self, state):
+        n = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
+        self._ctx = _ctx_for(self.maze, self.s_global)
+        pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None])
+        return self._ctx.local_map(pose, n, self.local_map_scale)
+
+    def plan(self):
+        if self.batch_size > 1:
+            return self._plan_batched()
+        start_time = time.time()
+        curr_time = time.time()
+        total_diffusion_time = 0
+        iter_num = 0
+        orig_prob_map = self.env.prob_map.copy()
+        has_obstacle_ahead = []
+        remain_init_path = None
+        if self.run_type > 0 and self.init_main_path is not None:
+            remain_init_path = self.extract_path_after_obstacle()
+        while (curr_time - start_time) < self.time_budget:
+            if self.iteration_cap is not None and iter_num >= self.iteration_cap:
+                break
+            sample_node = self._sample_state(remain_init_path)
+            curr_node = self.nearest_node(sample_node)
+            curr_state = curr_node.state
+            full_action_seq = None
+            full_states_seq = None
+            done = False
+            prev_actions = curr_node.parent_action_seq
+            prev_states = curr_state[None, None, :] if curr_node.parent_states_seq is None else curr_node.parent_states_seq
+            edge_length = self.prop_duration_schedule[
+                int(np.clip(curr_node.num_visit, 0, len(self.prop_duration_schedule) - 1))]
+            curr_node.num_visit += 1
+            goal = self._pick_goal(sample_node)
+            for _ in range(edge_length // self.action_horizon):
+                iter_num += 1
+                local_map = self._local_map(curr_state)
+                t0 = time.time()
+                sampled = self.sampler(prev_states, prev_actions=prev_actions, goal=goal,
+                                       local_map=local_map)[0, :self.action_horizon]
+                total_diffusion_time += time.time() - t0
+                curr_state, done, chunk_actions, chunk_states = self.propagate_action_sequence_env(curr_state, sampled)
+                if done is None:  # collision: the whole edge is dropped
+                    curr_state = None
+                    break
+                full_action_seq = chunk_actions if full_action_seq is None else np.concatenate((full_action_seq, chunk_actions))
+                prev_actions = chunk_actions
+                full_states_seq = chunk_states if full_states_seq is None else \
+                    np.concatenate((full_states_seq, chunk_states), axis=1)
+                prev_states = chunk_states
+                if done:
+                    break
+            if curr_state is not None and done is not None:
+                keep = ~(full_action_seq == 0).all(axis=1)
+                full_action_seq = full_action_seq[keep]
+                keep = ~(full_states_seq[0] == 0).all(axis=1)
+                full_states_seq = full_states_seq[0, keep][np.newaxis]
+                new_node = Node(curr_state, full_action_seq, full_states_seq, parent=curr_node)
+                self._insert(new_node)
+                has_obstacle_ahead.append(False if self.run_type == 0 else self.check_obstacle_ahead(curr_state))
+                if done:
+                    self.env.prob_map = orig_prob_map
+                    return self.handle_goal_reached(new_node, iter_num, start_time)
+            curr_time = time.time()
+        return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)
+
+    def _finish_without_goal(self, has_obstacle_ahead, iter_num, start_time, orig_prob_map):
+        """Budget exhausted (RRT.py:220-257): return the path to the best node."""
+        if np.all(has_obstacle_ahead):  # also true for an empty list, like the reference
+            self.env.prob_map = orig_prob_map
+            self.results["iterations"] = iter_num
+            self.results["number_of_nodes"] = len(self.node_list)
+            return None, None
+        nodes = self.node_list[1:]
+        ahead = np.array(has_obstacle_ahead, dtype=bool)
+        if self.run_type == 0 or self.init_main_path is None:
+            n = len(nodes)
+            idx = int(self._ctx.goal_cost_argmin(self._tree.x[1:1 + n], self._tree.y[1:1 + n], self.goal_state[:2],
+                                                 torch.as_tensor(ahead))[0])
+            best = nodes[idx]
+        else:
+            along = np.array([int(np.argmin(np.linalg.norm(nd.state[:2] - self.init_main_path[:, :2], axis=1)))
+                              if not ahead[i] else -1 for i, nd in enumerate(nodes)])
+            best = nodes[int(np.argmax(along))]
+        self.env.prob_map = orig_prob_map
+        return self.handle_goal_reached(best, iter_num, start_time)
+
+    # ---- batched expansion --------------------------------------------------------------------
+    def _plan_batched(self):
+        from ..expansion import TreeExpander
+        start_time = time.time()
+        B = self.batch_size
+        smp = self.sampler
+        n_map = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
+        ctx = smp._context()
+        self._ctx = _ctx_for(self.maze, self.s_global)
+        exp = TreeExpander(ctx, smp.metadata, n_map, self.local_map_scale, num_diffusion_iters=smp.num_diffusion_iters,
+                           pred_horizon=smp.pred_horizon, action_horizon=self.action_horizon, action_dim=smp.action_dim)
+        mean = torch.as_tensor(smp.metadata["Actions_mean"].astype(np.float32), device=ctx.device)
+        iter_num = 0
+        has_obstacle_ahead = []
+        orig_prob_map = self.env.prob_map.copy()
+        goal_xy = np.asarray(self.env.goal, dtype=np.float64)
+        h = self.action_horizon
+        while (time.time() - start_time) < self.time_budget:
+            if self.iteration_cap is not None and iter_num >= self.iteration_cap:
+                break
+            samples = np.concatenate([self._sample_state(None) for _ in range(B)], axis=0)
+            parents = self.nearest_node_batch(samples)
+            goals = np.stack([self._pick_goal(samples[i:i + 1]) for i in range(B)]).astype(np.float32)
+            for p in parents:
+                p.num_visit += 1
+            edge_length = self.prop_duration_schedule[0]
+            states = torch.as_tensor(np.stack([p.state for p in parents]).astype(np.float32), device=ctx.device)
+            # previous action = last action of the parent's edge; roots have none -> the action mean, whose
+            # normalised value is 0, which is what the reference feeds for prev_actions=None
+            prev = torch.stack([mean if p.parent_action_seq is None or len(p.parent_action_seq) == 0 else
+                                torch.as_tensor(np.asarray(p.parent_action_seq[-1], dtype=np.float32), device=ctx.device)
+                                for p in parents])
+            goals_d = torch.as_tensor(goals, device=ctx.device)
+            alive = torch.ones(B, dtype=torch.bool, device=ctx.device)
+            reached = torch.zeros(B, dtype=torch.bool, device=ctx.device)
+            chunks = []  # per chunk: (start states, actions, trajectory, took-part mask, steps taken)
+            for _ in range(edge_length // h):
+                iter_num += int(alive.sum())
+                lm = ctx.local_map(states, n_map, self.local_map_scale, bf16_signed=True)
+                cond = ctx.build_cond_car(states, prev, goals_d, smp.metadata, float(n_map))
+                noise = torch.randn((B, smp.pred_horizon, smp.action_dim), device=ctx.device)
+                a = ctx.fm_sample(noise, cond, lm, smp.num_diffusion_iters, smp.metadata["Actions_mean"],
+                                  smp.metadata["Actions_std"])
+                res = ctx.propagate_collide(states, a, goal_xy, S=h, want_traj=True)
+                coll = res["first_coll"] >= 0
+                done = res["done_step"] >= 0
+                took = alive & ~coll                      # candidates whose chunk is kept
+                steps = torch.where(done, res["done_step"] + 1, torch.full_like(res["done_step"], h))
+                chunks.append((states, a[:, :h], res["traj"], took, steps))
+                reached = reached | (took & done)
+                alive = took & ~done                      # a collision drops the whole edge (RRT.py:179-184)
+                states = torch.where(took[:, None], res["final"], states)
+                prev = torch.where(took[:, None], a[:, h - 1], prev)
+                if not bool(alive.any()):
+                    break
+            ok = (alive | reached).cpu().numpy()
+            if ok.any():
+                reached_h = reached.cpu().numpy()
+                fin = states.cpu().numpy().astype(np.float64)
+                host = [(s0.cpu().numpy().astype(np.float64), a.cpu().numpy().astype(np.float64),
+                         t.cpu().numpy().astype(np.float64), m.cpu().numpy(), n.cpu().numpy())
+                        for s0, a, t, m, n in chunks]
+                for b in np.nonzero(ok)[0]:
+                    a_seq, s_seq = [], []
+                    for s0, a_np, t_np, m_np, n_np in host:
+                        if not m_np[b]:
+                            break
+                        n = int(n_np[b])
+                        a_seq.append(a_np[b, :n])
+                        s_seq.append(s0[b][None])          # every chunk starts with its start state,
+                        s_seq.append(t_np[b, :n])          # like the reference's states_sequence
+                        if n < h:
+                            break
+                    node = Node(fin[b], np.concatenate(a_seq), np.concatenate(s_seq)[None], parent=parents[b])
+                    self._insert(node)
+                    has_obstacle_ahead.append(False if self.run_type == 0 else self.check_obstacle_ahead(fin[b]))
+                    if reached_h[b]:
+                        self.env.prob_map = orig_prob_map
+                        return self.handle_goal_reached(node, iter_num, start_time)
+        return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)

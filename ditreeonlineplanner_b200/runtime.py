@@ -76,6 +76,9 @@ class Context:
         self._check(self.lib.dt_profile_end(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_csv(self, path):
+        self._check(self.lib.dt_profile_csv(self.h, str(path).encode()))
+
     @property
     def launches(self):
         return int(self.lib.dt_launch_count(self.h))

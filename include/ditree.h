@@ -182,6 +182,9 @@ int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, in
  * synchronises the device and returns the summed kernel time (ms) and the number of launches. */
 int dt_profile_begin(dt_ctx* ctx);
 int dt_profile_end(dt_ctx* ctx, double* gemm_ms_out, int64_t* gemm_launches_out);
+/* Write the per-launch records of the last dt_profile_begin/end window as CSV
+ * (index, BN, epilogue, group width, M rows, N, K, milliseconds, TFLOP/s). */
+int dt_profile_csv(dt_ctx* ctx, const char* path);
 
 /* Number of kernels this library launched since the ctx was created (bench.py's gpu_launches). */
 int64_t dt_launch_count(dt_ctx* ctx);

@@ -19,6 +19,7 @@ ap.add_argument("--ode-steps", type=int, default=10)
 ap.add_argument("--rollout", type=int, default=50)
 ap.add_argument("--denoiser", default="large")
 ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--csv", default=None, help="write per-GEMM-launch timings (CUDA events) to this CSV")
 a = ap.parse_args()
 grid = load_maze("boxes").astype(np.float32)
 ctx = Context(0)
@@ -29,7 +30,13 @@ exp = TreeExpander(ctx, load_metadata("carmaze"), 20, 0.2, num_diffusion_iters=a
 st, prev = synth_candidates(grid, a.batch, 1000)
 st, prev = torch.as_tensor(st).cuda(), torch.as_tensor(prev).cuda()
 noise = torch.randn((a.batch, 64, 2), device="cuda")
-for _ in range(a.passes):
+for i in range(a.passes):
+    if i == a.passes - 1 and a.csv:
+        ctx.profile_begin()
     res = exp.expand_device(st, prev, goal_of(grid), noise=noise)
 torch.cuda.synchronize()
+if a.csv:
+    ms, n = ctx.profile_end()
+    ctx.profile_csv(a.csv)
+    print("gemm ms", ms, "launches", n)
 print("launches", ctx.launches, "ok edges", int((res["first_coll"] < 0).sum()))

@@ -1,0 +1,116 @@
+"""Scenario-suite sharding: the unit of work is one (scenario row, run index) pair of
+the reference's benchmark loop (run_scenarios.py:202,336-395).  A single tree stays on one GPU;
+ranks take disjoint units, there is no data-path collective, and the per-run result rows (the
+reference's CSV fields, run_scenarios.py:392-395) are gathered once with ``all_gather``.
+
+Deliberate, documented deviation from the reference: it seeds the three RNG streams once and
+lets them run across scenarios (run_scenarios.py:86-90); here every unit is seeded from
+(base seed, scenario index, run index) so results do not depend on the number of GPUs.
+"""
+from __future__ import annotations
+
+import random
+import time
+
+import numpy as np
+import torch
+
+from .data import load_maze, load_scenarios
+
+ROW_FIELDS = ["iteration", "success", "runtime", "trajectory_length", "trajectory_time", "avg_velocity",
+              "num_states_in_tree", "num_RRT_iterations", "ctrl_effort_max", "ctrl_effort_mean", "ctrl_effort_std"]
+
+
+def all_units(n_scenarios, total_runs, weights=None):
+    """Every (scenario, run) unit, heaviest scenario first (weights default to equal)."""
+    order = list(range(n_scenarios))
+    if weights is not None:
+        order.sort(key=lambda i: -weights[i])
+    return [(s, r) for r in range(total_runs) for s in order]
+
+
+def shard_units(n_scenarios, total_runs, rank, world, weights=None):
+    """Units of `rank`: round-robin over the weight-sorted list, so every rank gets the same mix."""
+    return all_units(n_scenarios, total_runs, weights)[rank::world]
+
+
+def unit_seed(scenario_idx, run_idx, base=42):
+    return (base * 1_000_003 + scenario_idx * 1009 + run_idx) % (2 ** 31 - 1)
+
+
+def seed_everything(seed):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def scenario_states(row, env):
+    """Start / goal states of a test_scenarios_car row (run_scenarios.py:239-246)."""
+    start_xy = env.cell_rowcol_to_xy(np.array([int(row["start_row"]), int(row["start_col"])]))
+    goal_xy = env.cell_rowcol_to_xy(np.array([int(row["goal_row"]), int(row["goal_col"])]))
+    start = np.array([start_xy[0], start_xy[1], np.deg2rad(float(row["start_deg"])), 0.0, 0.0, 0.0])
+    goal = np.array([goal_xy[0], goal_xy[1], 0.0, 0.0, 0.0, 0.0])
+    return start, goal
+
+
+def result_row(run_idx, path, actions, results, runtime):
+    """The reference's CSV row for one run (run_scenarios.py:345-395)."""
+    if path is not None:
+        length = float(np.sum(np.linalg.norm(np.diff(path[:, :2], axis=0), axis=1)))
+        vel = float(np.mean(np.sqrt(np.square(path[:, 2]) + np.square(path[:, 3]))))
+        effort = np.linalg.norm(actions, axis=1)
+        return [run_idx + 1, 1, runtime, length, results.get("path_time", 0.0), vel, results["number_of_nodes"],
+                results["iterations"], float(effort.max()), float(effort.mean()), float(effort.std())]
+    return [run_idx + 1, 0, runtime, -1, 0, -1, -1, results["iterations"], -1, -1, -1]
+
+
+def run_car_unit(row, scenario_idx, run_idx, sampler, time_budget, planner_kwargs=None):
+    """One (scenario, run): build env + planner exactly as the reference driver does and plan."""
+    from .car_env import CarEnv
+    from .planners.RRT import RRT_Planner
+    maze = load_maze(row["maze_name"])
+    env = CarEnv(maze_map=maze, collision_checking=False)
+    start, goal = scenario_states(row, env)
+    kw = dict(env_id="carmaze", environment=env, sampler=sampler, prediction_type="actions", action_horizon=8,
+              local_map_size=20, local_map_scale=0.2, global_map_scale=1.0, goal_conditioning_bias=0.85,
+              prop_duration=[64], time_budget=time_budget, max_iter=300, verbose=False)
+    kw.update(planner_kwargs or {})
+    planner = RRT_Planner(start, goal, **kw)
+    seed_everything(unit_seed(scenario_idx, run_idx))
+    t0 = time.time()
+    planner.reset()
+    path, actions = planner.plan()
+    return result_row(run_idx, path, actions, planner.results, time.time() - t0)
+
+
+def gather_rows(local_units, local_rows, n_units_total, device, world):
+    """all_gather the fixed-size result rows; returns {(scenario, run): row} on every rank."""
+    import torch.distributed as dist
+    per_rank = (n_units_total + world - 1) // world
+    buf = torch.full((per_rank, 2 + len(ROW_FIELDS)), float("nan"), dtype=torch.float32, device=device)
+    for i, ((s, r), row) in enumerate(zip(local_units, local_rows)):
+        buf[i, 0], buf[i, 1] = s, r
+        buf[i, 2:] = torch.as_tensor(row, dtype=torch.float32)
+    if world > 1:
+        out = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(out, buf)
+        allbuf = torch.cat(out).cpu().numpy()
+    else:
+        allbuf = buf.cpu().numpy()
+    table = {}
+    for rec in allbuf:
+        if not np.isnan(rec[0]):
+            table[(int(rec[0]), int(rec[1]))] = rec[2:].tolist()
+    return table
+
+
+def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car", rank=0, world=1, device="cuda",
+              planner_kwargs=None, unit_fn=run_car_unit):
+    """Run this rank's share of the suite and gather everybody's rows.  -> (table, seconds)."""
+    rows = load_scenarios(kind)
+    weights = [int(np.prod(load_maze(r["maze_name"]).shape)) for r in rows]
+    mine = shard_units(len(rows), total_runs, rank, world, weights)
+    t0 = time.time()
+    local = [unit_fn(rows[s], s, r, sampler, time_budget, planner_kwargs) for s, r in mine]
+    table = gather_rows(mine, local, len(rows) * total_runs, device, world)
+    return table, time.time() - t0

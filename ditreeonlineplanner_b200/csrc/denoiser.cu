@@ -85,8 +85,7 @@ struct dt_denoiser {
 // small CUDA-core kernels around the GEMMs
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float mishf(float x) {
-  if (x > 20.0f) return x;
-  const float e = __expf(x);
+  const float e = __expf(fminf(x, 20.0f));
   const float n = e * (e + 2.0f);
   return x * __fdividef(n, n + 2.0f);
 }

@@ -197,4 +197,82 @@ __device__ __forceinline__ int dt_car_test(const uint8_t* __restrict__ grid, int
   const int raises = ((a | b) & 4) && !((a & 8) && (b & 8));
   return ((a | b) & 1) | (raises ? 4 : 0);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Exactness-preserving fast path.  The exact test above spends most of its time in the float64
+// sincos and in eight hypot calls.  Here the heading's sine / cosine come from fp32 sincosf
+// (|error| <= 2 ulp ~ 1.2e-7, i.e. <= 1e-8 m on the 0.075 m ball offset) and every decision the
+// reference takes (cell index floors, the four side comparisons, the four corner distances) is
+// evaluated with a guard band DT_EPS = 1e-7 m >> that error.  If every decision is clear of its
+// threshold by more than the guard band, the outcome is provably the one the exact float64 code
+// produces; otherwise (probability ~1e-5 per state) the exact code runs.  Corner distances use
+// d^2 vs r^2 instead of hypot, and only when the diagonal cell can matter.
+// ---------------------------------------------------------------------------------------------
+#define DT_EPS 1.0e-7
+#define DT_AMBIG 16
+
+__device__ __forceinline__ int dt_ball_test_guarded(const uint8_t* __restrict__ grid, int R, int C, double ax,
+                                                    double ay) {
+  const double r = 0.1;
+  const double cx = 0.5 * (double)C, cy = 0.5 * (double)R;  // cell size 1
+  const double u = cy - ay, w = ax + cx;
+  const double fu = floor(u), fw = floor(w);
+  const double du = u - fu, dw = w - fw;  // position inside the cell, in [0, 1)
+  int amb = (du < DT_EPS) | (du > 1.0 - DT_EPS) | (dw < DT_EPS) | (dw > 1.0 - DT_EPS);
+  if (!(fu > -1.0e9 && fu < 1.0e9 && fw > -1.0e9 && fw < 1.0e9)) return amb ? DT_AMBIG : 2;
+  const int row = (int)fu, col = (int)fw;
+  if (row < 0 || row >= R || col < 0 || col >= C) return amb ? DT_AMBIG : 2;
+  int hit = grid[row * C + col] == 1;
+  // distances to the four cell edges: right = 1 - dw, left = dw, top = du (y grows upwards, rows down), bottom = 1 - du
+  const double e_r = 1.0 - dw, e_l = dw, e_t = du, e_b = 1.0 - du;
+  const int cR = dt_clampi(col + 1, 0, C - 1), cL = dt_clampi(col - 1, 0, C - 1);
+  const int rU = dt_clampi(row - 1, 0, R - 1), rD = dt_clampi(row + 1, 0, R - 1);
+  const int wR = grid[row * C + cR] == 1, wL = grid[row * C + cL] == 1;
+  const int wU = grid[rU * C + col] == 1, wD = grid[rD * C + col] == 1;
+  // side tests: ball reaches past the edge  <=>  edge distance < r
+  hit |= (e_r < r) & wR;
+  hit |= (e_l < r) & wL;
+  hit |= (e_t < r) & wU;
+  hit |= (e_b < r) & wD;
+  amb |= (fabs(e_r - r) < DT_EPS) & wR;
+  amb |= (fabs(e_l - r) < DT_EPS) & wL;
+  amb |= (fabs(e_t - r) < DT_EPS) & wU;
+  amb |= (fabs(e_b - r) < DT_EPS) & wD;
+  int err = hit ? 8 : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double ex = (k & 1) ? e_l : e_r;   // TR, TL, BR, BL
+    const double ey = (k & 2) ? e_b : e_t;
+    const int ci = row + ((k & 2) ? 1 : -1);
+    const int cj = col + ((k & 1) ? -1 : 1);
+    const int outside = (ci < 0) | (ci >= R) | (cj < 0) | (cj >= C);
+    const int ci_c = dt_clampi(ci, 0, R - 1);
+    const int cj_c = dt_clampi(cj, 0, R - 1);  // sic: clipped with the ROW count (map_utils.py:326)
+    if (cj_c > C - 1) {
+      err |= 4;
+      continue;
+    }
+    hit |= outside;
+    if (grid[ci_c * C + cj_c] == 1 && ex < r + DT_EPS && ey < r + DT_EPS) {
+      const double d2 = ex * ex + ey * ey;
+      hit |= d2 < r * r;
+      amb |= fabs(d2 - r * r) < 4.0 * r * DT_EPS;
+    }
+  }
+  return amb ? DT_AMBIG : (hit | err);
+}
+
+__device__ __forceinline__ int dt_car_test_fast(const uint8_t* __restrict__ grid, int R, int C, float xf, float yf,
+                                                float thf) {
+  float snf, csf;
+  sincosf(thf, &snf, &csf);
+  const double ox = 0.075 * (double)csf, oy = 0.075 * (double)snf;
+  const double x = (double)xf, y = (double)yf;
+  const int a = dt_ball_test_guarded(grid, R, C, x + ox, y + oy);
+  const int b = dt_ball_test_guarded(grid, R, C, x - ox, y - oy);
+  if ((a | b) & DT_AMBIG) return dt_car_test(grid, R, C, xf, yf, thf);  // rare: decide with the exact code
+  if ((a | b) & 2) return 1;
+  const int raises = ((a | b) & 4) && !((a & 8) && (b & 8));
+  return ((a | b) & 1) | (raises ? 4 : 0);
+}
 #endif  // __CUDACC__

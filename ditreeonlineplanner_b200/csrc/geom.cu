@@ -16,7 +16,7 @@ k_collide_car(MapView m, const float* __restrict__ x, const float* __restrict__ 
   __shared__ uint64_t bar;
   dt_stage_map(s_map, &bar, m);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = dt_car_test(s_map, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
+    const int r = dt_car_test_fast(s_map, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
     if (r & 4) atomicMin(status, DT_E_INDEX);
     out[i] = (uint8_t)(r & 1);
   }

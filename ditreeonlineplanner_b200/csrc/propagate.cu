@@ -78,8 +78,10 @@ k_propagate_collide(MapView m, PropArgs a, int* __restrict__ status) {
         bicycle_euler(x, y, psi, v, D, dl, u0, u1);
         // goal test (car_env.py:341-350) and collision (planners/base_planner.py:306) on the new state
         const double ex = xsub((double)x, gx), ey = xsub((double)y, gy);
-        const bool in_goal = __dsqrt_rn(xadd(xmul(ex, ex), xmul(ey, ey))) < 0.5;
-        const int c = dt_car_test(s_map, m.rows, m.cols, x, y, psi);
+        // ||p - goal|| < 0.5: compare squares, and take the square root only on the knife edge
+        const double d2 = xadd(xmul(ex, ex), xmul(ey, ey));
+        const bool in_goal = (fabs(d2 - 0.25) < 1.0e-9) ? (__dsqrt_rn(d2) < 0.5) : (d2 < 0.25);
+        const int c = dt_car_test_fast(s_map, m.rows, m.cols, x, y, psi);
         if (c & 4) atomicMin(status, DT_E_INDEX);
         const bool coll = (c & 1) != 0;
         if (coll && first < 0) first = i;

@@ -275,4 +275,105 @@ __device__ __forceinline__ int dt_car_test_fast(const uint8_t* __restrict__ grid
   const int raises = ((a | b) & 4) && !((a & 8) && (b & 8));
   return ((a | b) & 1) | (raises ? 4 : 0);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Second-generation fast path: per-cell neighbourhood masks + fp32 in-cell geometry.
+//
+// dt_build_nbr precomputes, once per block, a 16-bit mask per grid cell with everything the
+// reference looks up around a ball whose centre lies in that cell (own cell, the 4 side cells with
+// the reference's index clipping, the 4 diagonal cells with its row-count column clip, the
+// "diagonal outside the grid" flags and the would-raise-IndexError flag).  The per-ball test is
+// then: float64 only to locate the cell and the in-cell offsets (du, dw in [0,1)), one 16-bit
+// shared load, and ~40 fp32 compare / FMA operations with the guard band below.  A decision
+// closer than the guard band to its threshold defers to the exact float64 code (dt_car_test).
+//   error budget on an in-cell offset: 1e-8 (fp32 sincos on the 0.075 m offset) + 6e-8 (fp32
+//   rounding of a value in [0,1)) < DT_EPSF = 4e-7.
+// ---------------------------------------------------------------------------------------------
+#define NB_SELF 1u
+#define NB_R 2u
+#define NB_L 4u
+#define NB_U 8u
+#define NB_D 16u
+#define NB_CW(k) (32u << (k))    // diagonal k (0 TR, 1 TL, 2 BR, 3 BL) is a wall
+#define NB_CO(k) (512u << (k))   // diagonal k lies outside the grid (collides regardless of distance)
+#define NB_ERR 8192u             // the reference would index out of range for a diagonal of this cell
+#define DT_EPSF 4.0e-7f
+
+__device__ __forceinline__ void dt_build_nbr(const uint8_t* __restrict__ grid, uint16_t* __restrict__ nbr, int R,
+                                             int C) {
+  for (int cell = threadIdx.x; cell < R * C; cell += blockDim.x) {
+    const int row = cell / C, col = cell - row * C;
+    unsigned m = grid[cell] == 1 ? NB_SELF : 0u;
+    m |= grid[row * C + dt_clampi(col + 1, 0, C - 1)] == 1 ? NB_R : 0u;
+    m |= grid[row * C + dt_clampi(col - 1, 0, C - 1)] == 1 ? NB_L : 0u;
+    m |= grid[dt_clampi(row - 1, 0, R - 1) * C + col] == 1 ? NB_U : 0u;
+    m |= grid[dt_clampi(row + 1, 0, R - 1) * C + col] == 1 ? NB_D : 0u;
+    for (int k = 0; k < 4; ++k) {
+      const int ci = row + ((k & 2) ? 1 : -1), cj = col + ((k & 1) ? -1 : 1);
+      const int cj_c = dt_clampi(cj, 0, R - 1);  // sic (map_utils.py:326)
+      if (cj_c > C - 1) {
+        m |= NB_ERR;
+        continue;
+      }
+      if ((ci < 0) | (ci >= R) | (cj < 0) | (cj >= C)) m |= NB_CO(k);
+      if (grid[dt_clampi(ci, 0, R - 1) * C + cj_c] == 1) m |= NB_CW(k);
+    }
+    nbr[cell] = (uint16_t)m;
+  }
+}
+
+// returns bit0 hit, bit1 out of bounds, bit2 would raise, bit3 hit before the diagonal stage, DT_AMBIG
+__device__ __forceinline__ int dt_ball_test_nbr(const uint16_t* __restrict__ nbr, int R, int C, double ax, double ay) {
+  const double u = 0.5 * (double)R - ay, w = ax + 0.5 * (double)C;
+  if (!(u >= 0.0 && u < (double)R && w >= 0.0 && w < (double)C)) {
+    const bool near = (u > -1.0e-6) && (u < (double)R + 1.0e-6) && (w > -1.0e-6) && (w < (double)C + 1.0e-6);
+    return near ? DT_AMBIG : 2;  // NaN lands here too (every comparison false) -> out of bounds
+  }
+  const double fu = floor(u), fw = floor(w);
+  const float du = (float)(u - fu), dw = (float)(w - fw);
+  const unsigned nb = nbr[(int)fu * C + (int)fw];
+  const float r = 0.1f;
+  const float e_r = 1.0f - dw, e_l = dw, e_t = du, e_b = 1.0f - du;
+  bool amb = (du < DT_EPSF) | (du > 1.0f - DT_EPSF) | (dw < DT_EPSF) | (dw > 1.0f - DT_EPSF);
+  bool hit = (nb & NB_SELF) != 0;
+  hit |= ((nb & NB_R) != 0) & (e_r < r);
+  hit |= ((nb & NB_L) != 0) & (e_l < r);
+  hit |= ((nb & NB_U) != 0) & (e_t < r);
+  hit |= ((nb & NB_D) != 0) & (e_b < r);
+  amb |= ((nb & NB_R) != 0) & (fabsf(e_r - r) < DT_EPSF);
+  amb |= ((nb & NB_L) != 0) & (fabsf(e_l - r) < DT_EPSF);
+  amb |= ((nb & NB_U) != 0) & (fabsf(e_t - r) < DT_EPSF);
+  amb |= ((nb & NB_D) != 0) & (fabsf(e_b - r) < DT_EPSF);
+  const int pre = hit ? 8 : 0;
+  hit |= (nb & (NB_CO(0) | NB_CO(1) | NB_CO(2) | NB_CO(3))) != 0;
+  if (nb & (NB_CW(0) | NB_CW(1) | NB_CW(2) | NB_CW(3))) {
+    const float r2 = r * r, g2 = 2.0f * r * DT_EPSF;
+    const float xr = e_r * e_r, xl = e_l * e_l, yt = e_t * e_t, yb = e_b * e_b;
+    const float d0 = xr + yt, d1 = xl + yt, d2 = xr + yb, d3 = xl + yb;
+    hit |= ((nb & NB_CW(0)) != 0) & (d0 < r2);
+    hit |= ((nb & NB_CW(1)) != 0) & (d1 < r2);
+    hit |= ((nb & NB_CW(2)) != 0) & (d2 < r2);
+    hit |= ((nb & NB_CW(3)) != 0) & (d3 < r2);
+    amb |= ((nb & NB_CW(0)) != 0) & (fabsf(d0 - r2) < g2);
+    amb |= ((nb & NB_CW(1)) != 0) & (fabsf(d1 - r2) < g2);
+    amb |= ((nb & NB_CW(2)) != 0) & (fabsf(d2 - r2) < g2);
+    amb |= ((nb & NB_CW(3)) != 0) & (fabsf(d3 - r2) < g2);
+  }
+  if (amb) return DT_AMBIG;
+  return (hit ? 1 : 0) | pre | ((nb & NB_ERR) ? 4 : 0);
+}
+
+__device__ __forceinline__ int dt_car_test_nbr(const uint8_t* __restrict__ grid, const uint16_t* __restrict__ nbr,
+                                               int R, int C, float xf, float yf, float thf) {
+  float snf, csf;
+  sincosf(thf, &snf, &csf);
+  const double ox = 0.075 * (double)csf, oy = 0.075 * (double)snf;
+  const double x = (double)xf, y = (double)yf;
+  const int a = dt_ball_test_nbr(nbr, R, C, x + ox, y + oy);
+  const int b = dt_ball_test_nbr(nbr, R, C, x - ox, y - oy);
+  if ((a | b) & DT_AMBIG) return dt_car_test(grid, R, C, xf, yf, thf);  // rare: decide with the exact code
+  if ((a | b) & 2) return 1;
+  const int raises = ((a | b) & 4) && !((a & 8) && (b & 8));
+  return ((a | b) & 1) | (raises ? 4 : 0);
+}
 #endif  // __CUDACC__

@@ -230,6 +230,29 @@ __global__ void k_im2col(const __nv_bfloat16* __restrict__ in, int64_t B, int H,
   }
 }
 
+// vectorised im2col for C % 8 == 0 (every encoder conv except conv1): one 16-byte copy per thread
+__global__ void k_im2col_v8(const __nv_bfloat16* __restrict__ in, int64_t B, int H, int W, int C, int k, int stride,
+                            int pad, int OH, int OW, __nv_bfloat16* __restrict__ out) {
+  const int c8n = C / 8;
+  const int64_t n = B * OH * OW * (int64_t)(k * k) * c8n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    int64_t r = i / c8n;
+    const int tap = (int)(r % (k * k));
+    r /= (k * k);
+    const int ox = (int)(r % OW);
+    int64_t r2 = r / OW;
+    const int oy = (int)(r2 % OH);
+    const int64_t b = r2 / OH;
+    const int ky = tap / k, kx = tap - ky * k;
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = *reinterpret_cast<const uint4*>(in + ((b * H + iy) * W + ix) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(out + (r * (int64_t)(k * k) + tap) * C + c8 * 8) = v;
+  }
+}
+
 // GroupNorm(C/16 groups) over (HW x 16 channels) per sample, optional residual add, optional ReLU.
 // x: (B, HW, C) bf16 conv output (bias-free convs in resnet).  One warp per (sample, group).
 __global__ void __launch_bounds__(256)
@@ -828,8 +851,13 @@ static int unet_body(dt_ctx* ctx, dt_denoiser* d, int64_t B, const float* film_t
 static int enc_conv(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bfloat16* in, int64_t B, int H, int W,
                     int Cin, int k, int stride, int pad, int OH, int OW, __nv_bfloat16* out, cudaStream_t st) {
   const int64_t rows = B * OH * OW;
-  k_im2col<<<ew_grid(rows * w.Ktot, ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
-  DT_LAUNCH_CHECK("k_im2col");
+  if (Cin % 8 == 0 && w.Ktot == k * k * Cin) {
+    k_im2col_v8<<<ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
+    DT_LAUNCH_CHECK("k_im2col_v8");
+  } else {
+    k_im2col<<<ew_grid(rows * w.Ktot, ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
+    DT_LAUNCH_CHECK("k_im2col");
+  }
   ConvGemm g;
   g.a[0] = ActSrc{d->col, w.Ktot, (int)rows, 1};
   g.n_src = 1;

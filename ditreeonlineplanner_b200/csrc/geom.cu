@@ -14,9 +14,12 @@ k_collide_car(MapView m, const float* __restrict__ x, const float* __restrict__ 
               int64_t stride, int64_t B, uint8_t* __restrict__ out, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
+  uint16_t* s_nbr = reinterpret_cast<uint16_t*>(s_map + m.bytes);
   dt_stage_map(s_map, &bar, m);
+  dt_build_nbr(s_map, s_nbr, m.rows, m.cols);
+  __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = dt_car_test_fast(s_map, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
+    const int r = dt_car_test_nbr(s_map, s_nbr, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
     if (r & 4) atomicMin(status, DT_E_INDEX);
     out[i] = (uint8_t)(r & 1);
   }
@@ -321,7 +324,7 @@ extern "C" int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const
   if (B <= 0) return DT_OK;
   if (!x || !y || !theta || !flags_out) return dt_fail(ctx, DT_E_ARG, "dt_collide_car: null pointer");
   MapView m = dt_map_view(ctx);
-  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(
+  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, 3 * m.bytes, (cudaStream_t)stream>>>(
       m, x, y, theta, stride, B, flags_out, ctx->d_status);
   DT_LAUNCH_CHECK("k_collide_car");
   return DT_OK;

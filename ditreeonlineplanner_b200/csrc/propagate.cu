@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(PROP_THREADS)
 k_propagate_collide(MapView m, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
+  uint16_t* s_nbr = reinterpret_cast<uint16_t*>(s_map + m.bytes);
   dt_stage_map(s_map, &bar, m);
+  dt_build_nbr(s_map, s_nbr, m.rows, m.cols);
+  __syncthreads();
   const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
   const double gx = (double)a.goal_x, gy = (double)a.goal_y;
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
@@ -81,7 +84,7 @@ k_propagate_collide(MapView m, PropArgs a, int* __restrict__ status) {
         // ||p - goal|| < 0.5: compare squares, and take the square root only on the knife edge
         const double d2 = xadd(xmul(ex, ex), xmul(ey, ey));
         const bool in_goal = (fabs(d2 - 0.25) < 1.0e-9) ? (__dsqrt_rn(d2) < 0.5) : (d2 < 0.25);
-        const int c = dt_car_test_fast(s_map, m.rows, m.cols, x, y, psi);
+        const int c = dt_car_test_nbr(s_map, s_nbr, m.rows, m.cols, x, y, psi);
         if (c & 4) atomicMin(status, DT_E_INDEX);
         const bool coll = (c & 1) != 0;
         if (coll && first < 0) first = i;
@@ -130,9 +133,12 @@ k_propagate_rows(MapView m, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint64_t bar;
   uint8_t* s_map = s_dyn;
-  float* s_act = reinterpret_cast<float*>(s_dyn + m.bytes);
+  uint16_t* s_nbr = reinterpret_cast<uint16_t*>(s_dyn + m.bytes);
+  float* s_act = reinterpret_cast<float*>(s_dyn + 3 * m.bytes);
   float* s_trj = s_act + PROP_THREADS * PROP_APITCH;
   dt_stage_map(s_map, &bar, m);
+  dt_build_nbr(s_map, s_nbr, m.rows, m.cols);
+  __syncthreads();
   const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
   const double gx = (double)a.goal_x, gy = (double)a.goal_y;
   const int tid = threadIdx.x;
@@ -164,7 +170,7 @@ k_propagate_rows(MapView m, PropArgs a, int* __restrict__ status) {
           const double ex = xsub((double)x, gx), ey = xsub((double)y, gy);
           const double d2 = xadd(xmul(ex, ex), xmul(ey, ey));
           const bool in_goal = (fabs(d2 - 0.25) < 1.0e-9) ? (__dsqrt_rn(d2) < 0.5) : (d2 < 0.25);
-          const int c = dt_car_test_fast(s_map, m.rows, m.cols, x, y, psi);
+          const int c = dt_car_test_nbr(s_map, s_nbr, m.rows, m.cols, x, y, psi);
           if (c & 4) atomicMin(status, DT_E_INDEX);
           const bool coll = (c & 1) != 0;
           if (coll && first < 0) first = c0 + i;
@@ -227,7 +233,7 @@ extern "C" int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_
   const bool rows2 = (a_comp == 1) && (a_step % 2 == 0) && (a_cand % 2 == 0) && (((uintptr_t)actions & 7) == 0);
   const bool traj_rows = !traj_out || (t_comp == 1 && t_step == 6);
   if (a_comp == 1 && a_step == 2 && traj_rows) {
-    const size_t smem = (size_t)m.bytes + (size_t)PROP_THREADS * (PROP_APITCH + PROP_TPITCH) * sizeof(float);
+    const size_t smem = (size_t)3 * m.bytes + (size_t)PROP_THREADS * (PROP_APITCH + PROP_TPITCH) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       DT_CUDA(cudaFuncSetAttribute(k_propagate_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -238,9 +244,9 @@ extern "C" int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_
     if (blocks2 > cap2) blocks2 = cap2;
     k_propagate_rows<<<(int)blocks2, PROP_THREADS, smem, st>>>(m, a, ctx->d_status);
   } else if (rows2) {
-    k_propagate_collide<false><<<(int)blocks, PROP_THREADS, m.bytes, st>>>(m, a, ctx->d_status);
+    k_propagate_collide<false><<<(int)blocks, PROP_THREADS, 3 * m.bytes, st>>>(m, a, ctx->d_status);
   } else {
-    k_propagate_collide<true><<<(int)blocks, PROP_THREADS, m.bytes, st>>>(m, a, ctx->d_status);
+    k_propagate_collide<true><<<(int)blocks, PROP_THREADS, 3 * m.bytes, st>>>(m, a, ctx->d_status);
   }
   DT_LAUNCH_CHECK("k_propagate_collide");
   return DT_OK;

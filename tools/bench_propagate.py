@@ -15,7 +15,8 @@ ctx = Context(0)
 ctx.set_map(grid)
 goal = goal_of(grid)
 S = 50
-for B in (4096, 1 << 16, 1 << 20, 1 << 22):
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None   # e.g. "soa,no traj" : one config at B = 2^20 (for ncu)
+for B in ((1 << 20,) if ONLY else (4096, 1 << 16, 1 << 20, 1 << 22)):
     st_np, _ = synth_candidates(grid, B, 5)
     st = torch.as_tensor(st_np).cuda()
     act = torch.randn((B, S, 2), device="cuda") * torch.tensor([1.006, 0.923], device="cuda") + torch.tensor([0.451, 0.0], device="cuda")
@@ -25,11 +26,13 @@ for B in (4096, 1 << 16, 1 << 20, 1 << 22):
                      ("rows,no traj", lambda: ctx.propagate_collide(st, act, goal, want_traj=False)),
                      ("soa+traj", lambda: ctx.propagate_collide(st_soa, act_soa, goal, soa=True)),
                      ("soa,no traj", lambda: ctx.propagate_collide(st_soa, act_soa, goal, soa=True, want_traj=False))):
-        for _ in range(3):
+        if ONLY and name != ONLY:
+            continue
+        for _ in range(1 if ONLY else 3):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10 if B >= (1 << 20) else 50
+        reps = 1 if ONLY else (10 if B >= (1 << 20) else 50)
         e0.record()
         for _ in range(reps):
             fn()

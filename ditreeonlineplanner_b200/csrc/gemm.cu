@@ -150,7 +150,10 @@ struct SmemPlan {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
   static constexpr int kRedFloats = 2 * 8 * 8 * 8 * 2;         // [parity][warp][segment][group][sum,sq]
-  static constexpr int kBytes = kStages * kStage + (kParamFloats + kRedFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kFilmSamples = 8;                       // FiLM rows staged per tile (tiles of >= 16-row samples)
+  static constexpr int kFilmFloats = kFilmSamples * 2 * BN;    // [sample][scale | shift][BN], per-step part pre-added
+  static constexpr int kBytes =
+      kStages * kStage + (kParamFloats + kRedFloats + kFilmFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 template <int BN, int EPI, int GW>
@@ -166,7 +169,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   uint8_t* base_ptr = smem_raw + (base - raw);
   float* s_par = reinterpret_cast<float*>(base_ptr + P::kStages * P::kStage);
   float* s_red = s_par + P::kParamFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + P::kRedFloats);
+  float* s_film = s_red + P::kRedFloats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_film + P::kFilmFloats);
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
   const uint32_t bar_full = dt_smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * P::kStages;
@@ -314,6 +318,20 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           s_par[4 * BN + i] = g.film_t ? g.film_t[g.N + n0 + i] : 0.f;
         }
       }
+      // FiLM rows of the samples in this tile (per-candidate + per-step parts pre-added), coalesced
+      const int ns = g.tiles_per_sample > 0 ? 1 : g.nb;
+      const bool film_smem = (EPI == EPI_GN_MISH) && g.film && ns <= P::kFilmSamples;
+      if (film_smem) {
+        const long long b_first = g.tiles_per_sample > 0 ? (long long)(m_tile / g.tiles_per_sample) : (long long)m_tile * g.nb;
+        for (int i = et; i < ns * 2 * BN; i += 256) {
+          const int smp = i / (2 * BN), rem = i - smp * 2 * BN;
+          const int part = rem / BN, col = rem - part * BN;
+          const long long bb = b_first + smp;
+          float v = g.film_t ? g.film_t[part * g.N + n0 + col] : 0.f;
+          if (bb < g.B) v += g.film[bb * g.film_ld + part * g.N + n0 + col];
+          s_film[i] = v;
+        }
+      }
       epi_bar_sync();
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -395,12 +413,28 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 
       // pass 2: normalise / activate / modulate and store this warp's half of the columns
       const int nh = n0 + half * HALF;
-      const float* film_row = (EPI == EPI_GN_MISH && g.film && valid) ? g.film + b * g.film_ld + nh : nullptr;
+      const float* film_row = (EPI == EPI_GN_MISH && g.film && valid && !film_smem) ? g.film + b * g.film_ld + nh : nullptr;
+      const int smp_in_tile = g.tiles_per_sample > 0 ? 0 : row / g.T;
+      const float* fs = s_film + smp_in_tile * 2 * BN + half * HALF;  // staged scale row; shift row at + BN
       const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + nh : nullptr;
+      uint4 res_next[4];
+      if (res_row) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) res_next[u] = __ldg(reinterpret_cast<const uint4*>(res_row + 8 * u));
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < HALF; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
+        uint4 res_cur[4];
+        if (res_row) {  // software pipeline: this chunk's residual was requested one iteration ago
+#pragma unroll
+          for (int u = 0; u < 4; ++u) res_cur[u] = res_next[u];
+          if (c0 + 32 < HALF) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) res_next[u] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32 + 8 * u));
+          }
+        }
         float y[32];
         if (EPI == EPI_GN_MISH) {
           // groups touched by this 32-column chunk: one when GW >= 32, else 32 / GW
@@ -425,7 +459,17 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
               y[j + e] = mish_f((v - cm[u]) * cr[u] * gam[e] + bet[e]);
             }
           }
-          if (film_row) {
+          if (film_smem) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(fs + c0 + j);
+              const float4 sh = *reinterpret_cast<const float4*>(fs + BN + c0 + j);
+              y[j + 0] = y[j + 0] * sc.x + sh.x;
+              y[j + 1] = y[j + 1] * sc.y + sh.y;
+              y[j + 2] = y[j + 2] * sc.z + sh.z;
+              y[j + 3] = y[j + 3] * sc.w + sh.w;
+            }
+          } else if (film_row) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + c0 + j));
@@ -445,7 +489,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         if (res_row) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const uint4 pk = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + j));
+            const uint4 pk = res_cur[j / 8];
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

@@ -92,6 +92,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// asynchronous 16-column TMEM load; the registers are only valid after tmem_wait() on the same array
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// tcgen05.wait::ld for all outstanding loads; the "+r" operands tie the loaded registers to the wait
+// so the compiler cannot consume them (or move them) before it
+__device__ __forceinline__ void tmem_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row atoms of
 // 1024 B (SBO = 64 x 16 B), LBO unused for swizzled K-major (canonical value 1), version 1.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -108,9 +127,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // exponent argument at 20 keeps n finite (2.4e17) and n / (n + 2) == 1 there, so mish(x) = x as it should;
 // no per-element branch means the 32 MUFU chains of a chunk overlap.
 __device__ __forceinline__ float mish_f(float x) {
-  const float e = __expf(fminf(x, 20.0f));
+  float e, inv;
+  const float a = fminf(x, 20.0f) * 1.4426950408889634f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
   const float n = e * (e + 2.0f);
-  return x * __fdividef(n, n + 2.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(n + 2.0f));
+  return x * (n * inv);
 }
 
 template <int NG>
@@ -282,14 +304,45 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): the pair splits
-    // the BN accumulator columns in halves, so each SM sub-partition has two epilogue warps to overlap
-    // TMEM loads, the Mish MUFU chain and the global FiLM / residual loads.
+    // the BN accumulator columns in halves.  TMEM is read in 16-column chunks, double-buffered in
+    // registers (the load of chunk c+1 is in flight while chunk c is processed); the per-column
+    // parameters and FiLM rows of the NEXT tile are prefetched into registers while this tile is
+    // processed, so their global-memory latency is never exposed.
     constexpr int HALF = BN / 2;
+    constexpr int CH = 16;
+    constexpr int NCH = HALF / CH;
     const int q = warp & 3;                 // TMEM lane quarter
     const int half = (warp - 2) >> 2;       // which half of the columns
     const int ew = warp - 2;                // 0..7
     const int row = q * 32 + lane;          // row inside the M tile
     const int et = threadIdx.x - 64;        // 0..255
+    const int pcol = et % BN;               // the column whose parameters this thread stages
+    const int ns = g.tiles_per_sample > 0 ? 1 : g.nb;  // samples per tile
+    const bool film_smem = (EPI == EPI_GN_MISH) && g.film && ns <= P::kFilmSamples;
+    constexpr int PF = (P::kFilmSamples * 2 * BN) / 256;  // FiLM values staged per thread (at most)
+    float pf_par[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float pf_film[PF];
+    auto prefetch = [&](int tile_) {
+      const int m_ = tile_ / g.num_n_tiles, n0_ = (tile_ - m_ * g.num_n_tiles) * BN;
+      pf_par[0] = g.bias ? __ldg(g.bias + n0_ + pcol) : 0.f;
+      if (EPI == EPI_GN_MISH) {
+        pf_par[1] = __ldg(g.gamma + n0_ + pcol);
+        pf_par[2] = __ldg(g.beta + n0_ + pcol);
+        pf_par[3] = g.film_t ? __ldg(g.film_t + n0_ + pcol) : 0.f;
+        pf_par[4] = g.film_t ? __ldg(g.film_t + g.N + n0_ + pcol) : 0.f;
+        if (film_smem) {
+          const long long b_first = g.tiles_per_sample > 0 ? (long long)(m_ / g.tiles_per_sample) : (long long)m_ * g.nb;
+#pragma unroll
+          for (int j = 0; j < PF; ++j) {
+            const int i = et + 256 * j;  // index into [sample][part][BN]; its column is pcol for every j
+            const int smp = i / (2 * BN), part = (i / BN) & 1;
+            const long long bb = b_first + smp;
+            pf_film[j] = (smp < ns && bb < g.B) ? __ldg(g.film + bb * g.film_ld + part * g.N + n0_ + pcol) : 0.f;
+          }
+        }
+      }
+    };
+    if ((int)blockIdx.x < total_tiles) prefetch(blockIdx.x);
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -306,33 +359,27 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         t = row % g.T;
       }
       const bool valid = (b < g.B) && (t < g.T);
-      // stage the per-column parameters of this N tile (previous tile's readers are past their last use:
-      // they have all arrived on the barrier below in the previous iteration before anyone gets here twice)
+      // publish this tile's (prefetched) parameters; the first barrier orders the previous tile's readers
       epi_bar_sync();
-      for (int i = et; i < BN; i += 256) {
-        s_par[i] = g.bias ? g.bias[n0 + i] : 0.f;
+      if (et < BN) {
+        s_par[et] = pf_par[0];
         if (EPI == EPI_GN_MISH) {
-          s_par[BN + i] = g.gamma[n0 + i];
-          s_par[2 * BN + i] = g.beta[n0 + i];
-          s_par[3 * BN + i] = g.film_t ? g.film_t[n0 + i] : 0.f;
-          s_par[4 * BN + i] = g.film_t ? g.film_t[g.N + n0 + i] : 0.f;
+          s_par[BN + et] = pf_par[1];
+          s_par[2 * BN + et] = pf_par[2];
         }
       }
-      // FiLM rows of the samples in this tile (per-candidate + per-step parts pre-added), coalesced
-      const int ns = g.tiles_per_sample > 0 ? 1 : g.nb;
-      const bool film_smem = (EPI == EPI_GN_MISH) && g.film && ns <= P::kFilmSamples;
       if (film_smem) {
-        const long long b_first = g.tiles_per_sample > 0 ? (long long)(m_tile / g.tiles_per_sample) : (long long)m_tile * g.nb;
-        for (int i = et; i < ns * 2 * BN; i += 256) {
-          const int smp = i / (2 * BN), rem = i - smp * 2 * BN;
-          const int part = rem / BN, col = rem - part * BN;
-          const long long bb = b_first + smp;
-          float v = g.film_t ? g.film_t[part * g.N + n0 + col] : 0.f;
-          if (bb < g.B) v += g.film[bb * g.film_ld + part * g.N + n0 + col];
-          s_film[i] = v;
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+          const int i = et + 256 * j;
+          if (i < ns * 2 * BN) s_film[i] = pf_film[j] + (((i / BN) & 1) ? pf_par[4] : pf_par[3]);
         }
+      } else if (EPI == EPI_GN_MISH && et < BN) {
+        s_par[3 * BN + et] = pf_par[3];
+        s_par[4 * BN + et] = pf_par[4];
       }
       epi_bar_sync();
+      if (tile + (int)gridDim.x < total_tiles) prefetch(tile + gridDim.x);  // in flight during this tile
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -340,33 +387,31 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
 
       float mean[NG], rstd[NG];
+      uint32_t rb[2][CH];
       if (EPI == EPI_GN_MISH) {
         float gs[NG], gq[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) gs[i] = gq[i] = 0.f;
         // pass 1: per-row partial sums of (acc + bias) and its square for the groups in this half
-        if (half == 0) {
+        tmem_ld16(taddr, rb[0]);
 #pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
+        for (int c = 0; c < NCH; ++c) {
+          tmem_wait(rb[c & 1]);
+          if (c + 1 < NCH) tmem_ld16(taddr + (c + 1) * CH, rb[(c + 1) & 1]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]) + sp[c0 + j];
-              gs[(c0 + j) / GW] += v;
-              gq[(c0 + j) / GW] += v * v;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < HALF; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]) + sp[c0 + j];
-              gs[(HALF + c0 + j) / GW] += v;
-              gq[(HALF + c0 + j) / GW] += v * v;
+          for (int j = 0; j < CH; ++j) {
+            const float v = __uint_as_float(rb[c & 1][j]) + sp[c * CH + j];
+            // column (half * HALF + c * CH + j) belongs to group index below; `half` is warp-uniform
+            const int gi0 = (c * CH + j) / GW, gi1 = (HALF + c * CH + j) / GW;
+            if (gi0 == gi1) {
+              gs[gi0] += v;
+              gq[gi0] += v * v;
+            } else if (half == 0) {
+              gs[gi0] += v;
+              gq[gi0] += v * v;
+            } else {
+              gs[gi1] += v;
+              gq[gi1] += v * v;
             }
           }
         }
@@ -417,28 +462,31 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const int smp_in_tile = g.tiles_per_sample > 0 ? 0 : row / g.T;
       const float* fs = s_film + smp_in_tile * 2 * BN + half * HALF;  // staged scale row; shift row at + BN
       const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + nh : nullptr;
-      uint4 res_next[4];
+      uint4 res_next[2];
       if (res_row) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) res_next[u] = __ldg(reinterpret_cast<const uint4*>(res_row + 8 * u));
+        res_next[0] = __ldg(reinterpret_cast<const uint4*>(res_row));
+        res_next[1] = __ldg(reinterpret_cast<const uint4*>(res_row + 8));
       }
-#pragma unroll 1
-      for (int c0 = 0; c0 < HALF; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        uint4 res_cur[4];
+      tmem_ld16(taddr, rb[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int c0 = c * CH;
+        tmem_wait(rb[c & 1]);
+        if (c + 1 < NCH) tmem_ld16(taddr + c0 + CH, rb[(c + 1) & 1]);
+        uint4 res_cur[2];
         if (res_row) {  // software pipeline: this chunk's residual was requested one iteration ago
-#pragma unroll
-          for (int u = 0; u < 4; ++u) res_cur[u] = res_next[u];
-          if (c0 + 32 < HALF) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) res_next[u] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32 + 8 * u));
+          res_cur[0] = res_next[0];
+          res_cur[1] = res_next[1];
+          if (c + 1 < NCH) {
+            res_next[0] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + CH));
+            res_next[1] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + CH + 8));
           }
         }
-        float y[32];
+        const uint32_t* r = rb[c & 1];
+        float y[CH];
         if (EPI == EPI_GN_MISH) {
-          // groups touched by this 32-column chunk: one when GW >= 32, else 32 / GW
-          constexpr int GPC = (GW >= 32) ? 1 : 32 / GW;
+          // groups touched by this chunk: one when GW >= 16, else 16 / GW
+          constexpr int GPC = (GW >= CH) ? 1 : CH / GW;
           float cm[GPC], cr[GPC];
 #pragma unroll
           for (int u = 0; u < GPC; ++u) {
@@ -446,7 +494,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             cr[u] = pick<NG>(rstd, (half * HALF + c0) / GW + u);
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < CH; j += 4) {
             const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
             const float4 ga = *reinterpret_cast<const float4*>(sp + BN + c0 + j);
             const float4 be = *reinterpret_cast<const float4*>(sp + 2 * BN + c0 + j);
@@ -454,14 +502,14 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
                         bet[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int u = (GW >= 32) ? 0 : (j + e) / GW;
+              const int u = (GW >= CH) ? 0 : (j + e) / GW;
               const float v = __uint_as_float(r[j + e]) + bia[e];
               y[j + e] = mish_f((v - cm[u]) * cr[u] * gam[e] + bet[e]);
             }
           }
           if (film_smem) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CH; j += 4) {
               const float4 sc = *reinterpret_cast<const float4*>(fs + c0 + j);
               const float4 sh = *reinterpret_cast<const float4*>(fs + BN + c0 + j);
               y[j + 0] = y[j + 0] * sc.x + sh.x;
@@ -471,7 +519,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             }
           } else if (film_row) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CH; j += 4) {
               const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + c0 + j));
               const float4 sh = __ldg(reinterpret_cast<const float4*>(film_row + g.N + c0 + j));
               const float4 ts = *reinterpret_cast<const float4*>(sp + 3 * BN + c0 + j);
@@ -484,11 +532,11 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(r[j]) + sp[c0 + j];
+          for (int j = 0; j < CH; ++j) y[j] = __uint_as_float(r[j]) + sp[c0 + j];
         }
         if (res_row) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < CH; j += 8) {
             const uint4 pk = res_cur[j / 8];
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
 #pragma unroll
@@ -501,13 +549,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         }
         if (EPI == EPI_PLAIN && g.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          for (int j = 0; j < CH; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (valid) {
           if (g.out_bf16) {
             __nv_bfloat16* o = g.out_bf16 + out_row * g.ldc + nh + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < CH; j += 8) {
               uint4 pk;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
@@ -518,7 +566,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           if (g.out_f32) {
             float* o = g.out_f32 + out_row * g.ldc + nh + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
         }
       }

@@ -16,13 +16,14 @@
 //               GroupNorm statistics are tile-local because a tile holds whole samples (M tile =
 //               128/T samples x T rows) and whole groups (BN is a multiple of the group width).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 
 #define BM 128
 #define BK 64
 #define GEMM_THREADS 320
-#define SPIN_LIMIT (1u << 27)
+#define SPIN_LIMIT (1u << 24)
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -65,6 +66,60 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants -----------------------------------------------------------
+// In a 2-CTA cluster the shared::cluster address of the even (leader) CTA's copy of a shared
+// variable is the local address with bit 24 cleared.
+#define DT_PEER_MASK 0xFEFFFFFFu
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  const unsigned long long hint = 0x1000000000000000ull;  // evict-normal
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(map), "r"(bar & DT_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  const unsigned long long hint = 0x14F0000000000000ull;  // evict-last: weights are re-read by every M tile
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar & DT_PEER_MASK), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((unsigned short)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the copy of `bar` that lives in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -164,12 +219,12 @@ struct GemmDev {
   long long ldc, out_b_stride, out_t_stride, out_off;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct SmemPlan {
   static constexpr int kStageA = BM * BK * 2;
-  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStageB = (BN / CG) * BK * 2;  // with a CTA pair each CTA stages half of the weight tile
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (192 * 1024 / kStage) > 8 ? 8 : (192 * 1024 / kStage);
   static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
   static constexpr int kRedFloats = 2 * 8 * 8 * 8 * 2;         // [parity][warp][segment][group][sum,sq]
   static constexpr int kFilmSamples = 8;                       // FiLM rows staged per tile (tiles of >= 16-row samples)
@@ -178,11 +233,17 @@ struct SmemPlan {
       kStages * kStage + (kParamFloats + kRedFloats + kFilmFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 };
 
-template <int BN, int EPI, int GW>
+// CG = 1: one CTA per tile (UMMA M = 128).  CG = 2: a CTA pair works on a 256-row tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256): each CTA loads its own 128 activation rows and HALF of the
+// weight tile, which cuts the L2 -> shared-memory traffic per MAC by a third and deepens the ring.
+template <int BN, int EPI, int GW, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
             const __grid_constant__ CUtensorMap mapW, const GemmDev g) {
-  using P = SmemPlan<BN>;
+  using P = SmemPlan<BN, CG>;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int n_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // tile-processing units (CTAs or pairs)
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   constexpr int NG = (EPI == EPI_GN_MISH) ? BN / GW : 1;
   static_assert(NG <= 8, "at most 8 GroupNorm groups per N tile");
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +271,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 256);
+      mbar_init(bar_tempty + 8 * a, 8 * CG);  // one elected arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -218,24 +279,34 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dt_smem_u32(s_tmem)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dt_smem_u32(s_tmem)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dt_smem_u32(s_tmem)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int total_tiles = g.num_m_tiles * g.num_n_tiles;
+  // tiles are (unit-level M tile, N tile); a unit-level M tile is CG * 128 rows, CTA `rank` owns its 128-row slice
+  const int unit_m_tiles = (g.num_m_tiles + CG - 1) / CG;
+  const int total_tiles = unit_m_tiles * g.num_n_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / g.num_n_tiles, n_tile = tile - m_tile * g.num_n_tiles;
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
+      const int um_tile = tile / g.num_n_tiles, n_tile = tile - um_tile * g.num_n_tiles;
+      const int m_tile = um_tile * CG + (int)rank;
       int b_base, t_base;
       if (g.tiles_per_sample > 0) {
         b_base = m_tile / g.tiles_per_sample;
@@ -252,9 +323,16 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (lane == 0) {
             const uint32_t sa = base + stage * P::kStage;
-            mbar_expect_tx(bar_full + 8 * stage, P::kStage);
-            tma_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
-            tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN);
+            if (CG == 2) {
+              // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
+              if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * P::kStage);
+              tma2_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
+              tma2_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN + (int)rank * (BN / 2));
+            } else {
+              mbar_expect_tx(bar_full + 8 * stage, P::kStage);
+              tma_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
+              tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN);
+            }
           }
           __syncwarp();
           if (++stage == P::kStages) {
@@ -265,40 +343,50 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128 * CG
+    constexpr uint32_t idesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < g.nkb_total; ++kb) {
-        mbar_wait(bar_full + 8 * stage, phase);
+    if (rank == 0) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = base + stage * P::kStage;
-          const uint64_t da = umma_desc(sa), db = umma_desc(sa + P::kStageA);
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < g.nkb_total; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + stage * P::kStage;
+            const uint64_t da = umma_desc(sa), db = umma_desc(sa + P::kStageA);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte address field
-            tc_mma(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the 16-byte address field
+              if (CG == 2) tc2_mma(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              else tc_mma(d_addr, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // free the smem slot (in both CTAs) when these MMAs retire; publish the accumulator after the last block
+            if (CG == 2) {
+              tc2_commit(bar_empty + 8 * stage);
+              if (kb == g.nkb_total - 1) tc2_commit(bar_tfull + 8 * acc);
+            } else {
+              tc_commit(bar_empty + 8 * stage);
+              if (kb == g.nkb_total - 1) tc_commit(bar_tfull + 8 * acc);
+            }
           }
-          tc_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
-          if (kb == g.nkb_total - 1) tc_commit(bar_tfull + 8 * acc);
+          __syncwarp();
+          if (++stage == P::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == P::kStages) {
-          stage = 0;
-          phase ^= 1;
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   } else {
@@ -323,7 +411,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     float pf_par[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     float pf_film[PF];
     auto prefetch = [&](int tile_) {
-      const int m_ = tile_ / g.num_n_tiles, n0_ = (tile_ - m_ * g.num_n_tiles) * BN;
+      const int um_ = tile_ / g.num_n_tiles, n0_ = (tile_ - um_ * g.num_n_tiles) * BN;
+      const int m_ = um_ * CG + (int)rank;
       pf_par[0] = g.bias ? __ldg(g.bias + n0_ + pcol) : 0.f;
       if (EPI == EPI_GN_MISH) {
         pf_par[1] = __ldg(g.gamma + n0_ + pcol);
@@ -342,12 +431,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         }
       }
     };
-    if ((int)blockIdx.x < total_tiles) prefetch(blockIdx.x);
+    if (unit < total_tiles) prefetch(unit);
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / g.num_n_tiles, n_tile = tile - m_tile * g.num_n_tiles;
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
+      const int um_tile = tile / g.num_n_tiles, n_tile = tile - um_tile * g.num_n_tiles;
+      const int m_tile = um_tile * CG + (int)rank;
       const int n0 = n_tile * BN;
       long long b;
       int t;
@@ -379,7 +469,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         s_par[4 * BN + et] = pf_par[4];
       }
       epi_bar_sync();
-      if (tile + (int)gridDim.x < total_tiles) prefetch(tile + gridDim.x);  // in flight during this tile
+      if (tile + n_units < total_tiles) prefetch(tile + n_units);  // in flight during this tile
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -570,9 +660,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         }
       }
-      // release the accumulator to the MMA warp
+      // release the accumulator to the (leader's) MMA warp: one elected arrival per warp
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -581,9 +675,12 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's MMAs read this CTA's smem / TMEM until here
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -646,32 +743,62 @@ static int make_w_map(dt_ctx* ctx, CUtensorMap* m, const __nv_bfloat16* w, int N
   return DT_OK;
 }
 
-template <int BN, int EPI, int GW>
-static int launch_gemm(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
-                       const GemmDev& d, cudaStream_t st) {
-  using P = SmemPlan<BN>;
+template <int BN, int EPI, int GW, int CG>
+static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                          const GemmDev& d, cudaStream_t st) {
+  using P = SmemPlan<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    DT_CUDA(cudaFuncSetAttribute(k_conv_gemm<BN, EPI, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    DT_CUDA(cudaFuncSetAttribute(k_conv_gemm<BN, EPI, GW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     attr_set = true;
   }
-  const int total = d.num_m_tiles * d.num_n_tiles;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;  // persistent: one CTA per SM
+  const int unit_tiles = ((d.num_m_tiles + CG - 1) / CG) * d.num_n_tiles;
+  const int max_units = ctx->sm_count / CG;  // persistent: one CTA (or CTA pair) per SM (pair)
+  const int units = unit_tiles < max_units ? unit_tiles : max_units;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = P::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->prof_on) {
-    cudaEvent_t e0 = dt_prof_event(ctx), e1 = dt_prof_event(ctx);
+    e0 = dt_prof_event(ctx);
+    e1 = dt_prof_event(ctx);
     if (e0 && e1) {
-      dt_ctx::ProfRec rec{BN, EPI, GW, (long long)d.B * d.T, d.N, (long long)d.nkb_total * BK, 0.f};
+      dt_ctx::ProfRec rec{BN, EPI, GW * 10 + CG, (long long)d.B * d.T, d.N, (long long)d.nkb_total * BK, 0.f};
       ctx->prof_recs.push_back(rec);
       cudaEventRecord(e0, st);
-      k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
-      cudaEventRecord(e1, st);
-      DT_LAUNCH_CHECK("k_conv_gemm");
-      return DT_OK;
     }
   }
-  k_conv_gemm<BN, EPI, GW><<<grid, GEMM_THREADS, P::kBytes, st>>>(a0, a1, w, d);
+  DT_CUDA(cudaLaunchKernelEx(&cfg, k_conv_gemm<BN, EPI, GW, CG>, a0, a1, w, d));
+  if (e0 && e1) cudaEventRecord(e1, st);
   DT_LAUNCH_CHECK("k_conv_gemm");
   return DT_OK;
+}
+
+template <int BN, int EPI, int GW>
+static int launch_gemm(dt_ctx* ctx, int cg, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                       const GemmDev& d, cudaStream_t st) {
+  if (cg == 2) return launch_gemm_cg<BN, EPI, GW, 2>(ctx, a0, a1, w, d, st);
+  return launch_gemm_cg<BN, EPI, GW, 1>(ctx, a0, a1, w, d, st);
+}
+
+// 1 = one CTA per tile, 2 = CTA pairs (default); DITREE_GEMM_CG=1 forces the single-CTA kernels (debugging)
+static int gemm_cta_group() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DITREE_GEMM_CG");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
 }
 
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
@@ -743,21 +870,23 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   } else {
     mA1 = mA0;
   }
-  rc = make_w_map(ctx, &mW, g.w, g.N, ktot, bn);
+  // CTA pairs need at least two 128-row tiles; tiny problems stay on one CTA
+  const int cg = (d.num_m_tiles >= 2) ? gemm_cta_group() : 1;
+  rc = make_w_map(ctx, &mW, g.w, g.N, ktot, bn / cg);
   if (rc) return rc;
 
   if (g.epi == EPI_PLAIN) {
-    if (bn == 256) return launch_gemm<256, EPI_PLAIN, 256>(ctx, mA0, mA1, mW, d, st);
-    if (bn == 128) return launch_gemm<128, EPI_PLAIN, 128>(ctx, mA0, mA1, mW, d, st);
-    return launch_gemm<64, EPI_PLAIN, 64>(ctx, mA0, mA1, mW, d, st);
+    if (bn == 256) return launch_gemm<256, EPI_PLAIN, 256>(ctx, cg, mA0, mA1, mW, d, st);
+    if (bn == 128) return launch_gemm<128, EPI_PLAIN, 128>(ctx, cg, mA0, mA1, mW, d, st);
+    return launch_gemm<64, EPI_PLAIN, 64>(ctx, cg, mA0, mA1, mW, d, st);
   }
   switch (g.group_width) {
-    case 8: return launch_gemm<64, EPI_GN_MISH, 8>(ctx, mA0, mA1, mW, d, st);
-    case 16: return launch_gemm<128, EPI_GN_MISH, 16>(ctx, mA0, mA1, mW, d, st);
-    case 32: return launch_gemm<256, EPI_GN_MISH, 32>(ctx, mA0, mA1, mW, d, st);
-    case 64: return launch_gemm<256, EPI_GN_MISH, 64>(ctx, mA0, mA1, mW, d, st);
-    case 128: return launch_gemm<256, EPI_GN_MISH, 128>(ctx, mA0, mA1, mW, d, st);
-    case 256: return launch_gemm<256, EPI_GN_MISH, 256>(ctx, mA0, mA1, mW, d, st);
+    case 8: return launch_gemm<64, EPI_GN_MISH, 8>(ctx, cg, mA0, mA1, mW, d, st);
+    case 16: return launch_gemm<128, EPI_GN_MISH, 16>(ctx, cg, mA0, mA1, mW, d, st);
+    case 32: return launch_gemm<256, EPI_GN_MISH, 32>(ctx, cg, mA0, mA1, mW, d, st);
+    case 64: return launch_gemm<256, EPI_GN_MISH, 64>(ctx, cg, mA0, mA1, mW, d, st);
+    case 128: return launch_gemm<256, EPI_GN_MISH, 128>(ctx, cg, mA0, mA1, mW, d, st);
+    case 256: return launch_gemm<256, EPI_GN_MISH, 256>(ctx, cg, mA0, mA1, mW, d, st);
   }
   return dt_fail(ctx, DT_E_UNSUPPORTED, "unsupported GroupNorm group width");
 }

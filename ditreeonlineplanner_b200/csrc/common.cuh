@@ -322,6 +322,8 @@ __device__ __forceinline__ void dt_build_nbr(const uint8_t* __restrict__ grid, u
   }
 }
 
+__device__ __forceinline__ unsigned dt_sign(float v) { return __float_as_uint(v) >> 31; }  // 1 if v < 0
+
 // returns bit0 hit, bit1 out of bounds, bit2 would raise, bit3 hit before the diagonal stage, DT_AMBIG
 __device__ __forceinline__ int dt_ball_test_nbr(const uint16_t* __restrict__ nbr, int R, int C, double ax, double ay) {
   const double u = 0.5 * (double)R - ay, w = ax + 0.5 * (double)C;
@@ -332,35 +334,23 @@ __device__ __forceinline__ int dt_ball_test_nbr(const uint16_t* __restrict__ nbr
   const double fu = floor(u), fw = floor(w);
   const float du = (float)(u - fu), dw = (float)(w - fw);
   const unsigned nb = nbr[(int)fu * C + (int)fw];
-  const float r = 0.1f;
+  const float r = 0.1f, r2 = r * r;
   const float e_r = 1.0f - dw, e_l = dw, e_t = du, e_b = 1.0f - du;
-  bool amb = (du < DT_EPSF) | (du > 1.0f - DT_EPSF) | (dw < DT_EPSF) | (dw > 1.0f - DT_EPSF);
-  bool hit = (nb & NB_SELF) != 0;
-  hit |= ((nb & NB_R) != 0) & (e_r < r);
-  hit |= ((nb & NB_L) != 0) & (e_l < r);
-  hit |= ((nb & NB_U) != 0) & (e_t < r);
-  hit |= ((nb & NB_D) != 0) & (e_b < r);
-  amb |= ((nb & NB_R) != 0) & (fabsf(e_r - r) < DT_EPSF);
-  amb |= ((nb & NB_L) != 0) & (fabsf(e_l - r) < DT_EPSF);
-  amb |= ((nb & NB_U) != 0) & (fabsf(e_t - r) < DT_EPSF);
-  amb |= ((nb & NB_D) != 0) & (fabsf(e_b - r) < DT_EPSF);
-  const int pre = hit ? 8 : 0;
-  hit |= (nb & (NB_CO(0) | NB_CO(1) | NB_CO(2) | NB_CO(3))) != 0;
-  if (nb & (NB_CW(0) | NB_CW(1) | NB_CW(2) | NB_CW(3))) {
-    const float r2 = r * r, g2 = 2.0f * r * DT_EPSF;
-    const float xr = e_r * e_r, xl = e_l * e_l, yt = e_t * e_t, yb = e_b * e_b;
-    const float d0 = xr + yt, d1 = xl + yt, d2 = xr + yb, d3 = xl + yb;
-    hit |= ((nb & NB_CW(0)) != 0) & (d0 < r2);
-    hit |= ((nb & NB_CW(1)) != 0) & (d1 < r2);
-    hit |= ((nb & NB_CW(2)) != 0) & (d2 < r2);
-    hit |= ((nb & NB_CW(3)) != 0) & (d3 < r2);
-    amb |= ((nb & NB_CW(0)) != 0) & (fabsf(d0 - r2) < g2);
-    amb |= ((nb & NB_CW(1)) != 0) & (fabsf(d1 - r2) < g2);
-    amb |= ((nb & NB_CW(2)) != 0) & (fabsf(d2 - r2) < g2);
-    amb |= ((nb & NB_CW(3)) != 0) & (fabsf(d3 - r2) < g2);
-  }
-  if (amb) return DT_AMBIG;
-  return (hit ? 1 : 0) | pre | ((nb & NB_ERR) ? 4 : 0);
+  // geometry mask in the bit layout of `nb`: bit set <=> the ball reaches past that edge / into that corner disc
+  const float xr = e_r * e_r, xl = e_l * e_l, yt = e_t * e_t, yb = e_b * e_b;
+  const float d0 = xr + yt, d1 = xl + yt, d2 = xr + yb, d3 = xl + yb;
+  const unsigned gm = (dt_sign(e_r - r) << 1) | (dt_sign(e_l - r) << 2) | (dt_sign(e_t - r) << 3) |
+                      (dt_sign(e_b - r) << 4) | (dt_sign(d0 - r2) << 5) | (dt_sign(d1 - r2) << 6) |
+                      (dt_sign(d2 - r2) << 7) | (dt_sign(d3 - r2) << 8);
+  const unsigned hits = (nb & NB_SELF) | (nb & gm & 0x1FEu) | (nb & (NB_CO(0) | NB_CO(1) | NB_CO(2) | NB_CO(3)));
+  // guard band, evaluated on the smallest margin of ALL decisions (also those whose neighbour cell is
+  // free -- that only defers a few more states to the exact code): cell boundaries, edges, corner discs
+  const float m_cell = fminf(fminf(e_r, e_l), fminf(e_t, e_b));
+  const float m_side = fminf(fminf(fabsf(e_r - r), fabsf(e_l - r)), fminf(fabsf(e_t - r), fabsf(e_b - r)));
+  const float m_corner = fminf(fminf(fabsf(d0 - r2), fabsf(d1 - r2)), fminf(fabsf(d2 - r2), fabsf(d3 - r2)));
+  if (fminf(m_cell, m_side) < DT_EPSF || m_corner < 2.0f * r * DT_EPSF) return DT_AMBIG;
+  const unsigned pre = (nb & NB_SELF) | (nb & gm & 0x1Eu);
+  return (hits ? 1 : 0) | (pre ? 8 : 0) | ((nb & NB_ERR) ? 4 : 0);
 }
 
 __device__ __forceinline__ int dt_car_test_nbr(const uint8_t* __restrict__ grid, const uint16_t* __restrict__ nbr,

@@ -157,10 +157,18 @@ k_propagate_rows(MapView m, PropArgs a, int* __restrict__ status) {
     for (int c0 = 0; c0 < a.S; c0 += PROP_CH) {
       const int cs = (a.S - c0 < PROP_CH) ? (a.S - c0) : PROP_CH;  // steps in this chunk
       // coalesced load of the chunk's actions: per candidate 2*cs contiguous floats
-      const int na = cs * 2;
-      for (int e = tid; e < nb * na; e += PROP_THREADS) {
-        const int c = e / na, off = e - c * na;
-        s_act[c * PROP_APITCH + off] = a.actions[(b0 + c) * a.a_cand + (int64_t)c0 * 2 + off];
+      if (cs == PROP_CH) {  // full chunk: compile-time divisors
+        constexpr int na = PROP_CH * 2;
+        for (int e = tid; e < nb * na; e += PROP_THREADS) {
+          const int c = e / na, off = e % na;
+          s_act[c * PROP_APITCH + off] = __ldg(a.actions + (b0 + c) * a.a_cand + (int64_t)c0 * 2 + off);
+        }
+      } else {
+        const int na = cs * 2;
+        for (int e = tid; e < nb * na; e += PROP_THREADS) {
+          const int c = e / na, off = e - c * na;
+          s_act[c * PROP_APITCH + off] = __ldg(a.actions + (b0 + c) * a.a_cand + (int64_t)c0 * 2 + off);
+        }
       }
       __syncthreads();
       for (int i = 0; i < cs; ++i) {
@@ -188,10 +196,18 @@ k_propagate_rows(MapView m, PropArgs a, int* __restrict__ status) {
       __syncthreads();
       // coalesced store of the chunk's trajectory rows: per candidate 6*cs contiguous floats
       if (a.traj) {
-        const int nt = cs * 6;
-        for (int e = tid; e < nb * nt; e += PROP_THREADS) {
-          const int c = e / nt, off = e - c * nt;
-          a.traj[(b0 + c) * a.t_cand + (int64_t)c0 * 6 + off] = s_trj[c * PROP_TPITCH + off];
+        if (cs == PROP_CH) {
+          constexpr int nt = PROP_CH * 6;
+          for (int e = tid; e < nb * nt; e += PROP_THREADS) {
+            const int c = e / nt, off = e % nt;
+            a.traj[(b0 + c) * a.t_cand + (int64_t)c0 * 6 + off] = s_trj[c * PROP_TPITCH + off];
+          }
+        } else {
+          const int nt = cs * 6;
+          for (int e = tid; e < nb * nt; e += PROP_THREADS) {
+            const int c = e / nt, off = e - c * nt;
+            a.traj[(b0 + c) * a.t_cand + (int64_t)c0 * 6 + off] = s_trj[c * PROP_TPITCH + off];
+          }
         }
       }
       // (the next chunk's first __syncthreads orders these reads before the staging rows are rewritten)

@@ -22,7 +22,8 @@
 
 #define BM 128
 #define BK 64
-#define GEMM_THREADS 320
+#define EPI_SPLIT 2                      // epilogue warps per TMEM lane quarter (column split)
+#define GEMM_THREADS (64 + 128 * EPI_SPLIT)
 #define SPIN_LIMIT (1u << 24)
 
 // ------------------------------------------------------------------------------------------
@@ -145,7 +146,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_SPLIT) : "memory"); }
 
 // asynchronous 16-column TMEM load; the registers are only valid after tmem_wait() on the same array
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -226,7 +227,7 @@ struct SmemPlan {
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (192 * 1024 / kStage) > 8 ? 8 : (192 * 1024 / kStage);
   static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
-  static constexpr int kRedFloats = 2 * 8 * 8 * 8 * 2;         // [parity][warp][segment][group][sum,sq]
+  static constexpr int kRedFloats = (4 * EPI_SPLIT) * 8 * 8 * 2;  // [warp][segment][group][sum,sq]
   static constexpr int kFilmSamples = 8;                       // FiLM rows staged per tile (tiles of >= 16-row samples)
   static constexpr int kFilmFloats = kFilmSamples * 2 * BN;    // [sample][scale | shift][BN], per-step part pre-added
   static constexpr int kBytes =
@@ -271,7 +272,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 8 * CG);  // one elected arrival per epilogue warp (of both CTAs)
+      mbar_init(bar_tempty + 8 * a, 4 * EPI_SPLIT * CG);  // one elected arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
@@ -396,18 +397,20 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     // registers (the load of chunk c+1 is in flight while chunk c is processed); the per-column
     // parameters and FiLM rows of the NEXT tile are prefetched into registers while this tile is
     // processed, so their global-memory latency is never exposed.
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / EPI_SPLIT;    // columns per epilogue warp
     constexpr int CH = 16;
     constexpr int NCH = HALF / CH;
+    static_assert(HALF % CH == 0, "column split must be a multiple of the TMEM chunk");
+    constexpr int NET = 128 * EPI_SPLIT;    // epilogue threads
     const int q = warp & 3;                 // TMEM lane quarter
-    const int half = (warp - 2) >> 2;       // which half of the columns
-    const int ew = warp - 2;                // 0..7
+    const int half = (warp - 2) >> 2;       // which slice of the columns (0 .. EPI_SPLIT-1)
+    const int ew = warp - 2;                // 0 .. 4*EPI_SPLIT-1
     const int row = q * 32 + lane;          // row inside the M tile
-    const int et = threadIdx.x - 64;        // 0..255
+    const int et = threadIdx.x - 64;        // 0 .. NET-1
     const int pcol = et % BN;               // the column whose parameters this thread stages
     const int ns = g.tiles_per_sample > 0 ? 1 : g.nb;  // samples per tile
     const bool film_smem = (EPI == EPI_GN_MISH) && g.film && ns <= P::kFilmSamples;
-    constexpr int PF = (P::kFilmSamples * 2 * BN) / 256;  // FiLM values staged per thread (at most)
+    constexpr int PF = (P::kFilmSamples * 2 * BN + NET - 1) / NET;  // FiLM values staged per thread (at most)
     float pf_par[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     float pf_film[PF];
     auto prefetch = [&](int tile_) {
@@ -423,7 +426,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           const long long b_first = g.tiles_per_sample > 0 ? (long long)(m_ / g.tiles_per_sample) : (long long)m_ * g.nb;
 #pragma unroll
           for (int j = 0; j < PF; ++j) {
-            const int i = et + 256 * j;  // index into [sample][part][BN]; its column is pcol for every j
+            const int i = et + NET * j;  // index into [sample][part][BN]; its column is pcol for every j
             const int smp = i / (2 * BN), part = (i / BN) & 1;
             const long long bb = b_first + smp;
             pf_film[j] = (smp < ns && bb < g.B) ? __ldg(g.film + bb * g.film_ld + part * g.N + n0_ + pcol) : 0.f;
@@ -461,7 +464,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       if (film_smem) {
 #pragma unroll
         for (int j = 0; j < PF; ++j) {
-          const int i = et + 256 * j;
+          const int i = et + NET * j;
           if (i < ns * 2 * BN) s_film[i] = pf_film[j] + (((i / BN) & 1) ? pf_par[4] : pf_par[3]);
         }
       } else if (EPI == EPI_GN_MISH && et < BN) {
@@ -491,17 +494,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             const float v = __uint_as_float(rb[c & 1][j]) + sp[c * CH + j];
-            // column (half * HALF + c * CH + j) belongs to group index below; `half` is warp-uniform
-            const int gi0 = (c * CH + j) / GW, gi1 = (HALF + c * CH + j) / GW;
-            if (gi0 == gi1) {
-              gs[gi0] += v;
-              gq[gi0] += v * v;
-            } else if (half == 0) {
-              gs[gi0] += v;
-              gq[gi0] += v * v;
-            } else {
-              gs[gi1] += v;
-              gq[gi1] += v * v;
+            // column (half * HALF + c * CH + j): its group index is compile-time per slice, `half` is warp-uniform
+#pragma unroll
+            for (int h = 0; h < EPI_SPLIT; ++h) {
+              if (half == h) {
+                gs[(h * HALF + c * CH + j) / GW] += v;
+                gq[(h * HALF + c * CH + j) / GW] += v * v;
+              }
             }
           }
         }
@@ -515,7 +514,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         }
         // ... then across warps through shared memory: the partner half always, other quarters when T > 32
-        float* red = s_red + (it & 1) * (8 * 8 * 8 * 2);
+        float* red = s_red;  // reuse across tiles is ordered by the two barriers at the top of the tile loop
         const int seg = lane / span;
         if ((lane % span) == 0) {
 #pragma unroll
@@ -533,8 +532,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           float a = 0.f, c = 0.f;
           for (int qq = q0; qq < q0 + wps; ++qq) {
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int w2 = ((qq + 2) & 3) + 4 * hh;  // ew of the warp with lane quarter qq, half hh
+            for (int hh = 0; hh < EPI_SPLIT; ++hh) {
+              const int w2 = ((qq + 2) & 3) + 4 * hh;  // ew of the warp with lane quarter qq, column slice hh
               a += red[((w2 * 8 + seg) * 8 + i) * 2 + 0];
               c += red[((w2 * 8 + seg) * 8 + i) * 2 + 1];
             }

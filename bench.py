@@ -150,6 +150,18 @@ def time_cpu(args, grid, meta, budget_s=15.0, steps=1, warmup=0):
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    # Only the final JSON line may reach stdout: libraries (e.g. NCCL's version banner) print there too,
+    # so fd 1 points at stderr until the result is ready.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)  # anything printed during teardown goes to stderr again
+
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -171,7 +183,7 @@ def main():
                            "Python reference itself cannot travel to the GPU box"},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------- our arm ----------------
@@ -312,7 +324,7 @@ def main():
                     "ms_per_step": e2e_ms, "api": "TreeExpander.expand(states, prev_actions, goal) with NumPy host arrays"},
             "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges,
             "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "clocks": clocks.summary()}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

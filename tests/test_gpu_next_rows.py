@@ -1,0 +1,101 @@
+"""Rows (f) of the scope table: SB3-free batched rollout, online scan / replan helpers, MPPI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import denoiser_ref as dref
+from oracle import ditree_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_sd():
+    return dref.init_params(seed=21, input_dim=2, cond_dim=7, emb_dim=400, down_dims=[64, 128, 256])
+
+
+def test_rollout_without_sb3(small_sd):
+    from ditreeonlineplanner_b200.rollout_manager import rollout
+    from ditreeonlineplanner_b200 import load_scenarios
+    torch.manual_seed(0)
+    res, frames = rollout("carmaze", "flow_matching", small_sd, None, max_episode_steps=40, num_diffusion_iters=1,
+                          obs_history=1, action_history=1, local_map_size=20, scale=0.2, pred_horizon=64,
+                          action_horizon=8, envs_per_scenario=8)
+    rows = load_scenarios("validation_scenarios_car")
+    assert len(res) == len(rows) and frames == []
+    for r in res:
+        assert set(r) == {"scenario_name", "maze", "start_rowcol", "goal_rowcol", "start_position", "goal_position",
+                          "best_dist", "step_to_completion", "trajectory", "collision_count"}
+        tr = r["trajectory"]
+        assert tr.shape == (8, 41, 8) and r["best_dist"].shape == (8,)
+        grid = np.asarray(r["maze"], np.float32)
+        for e in range(8):
+            # replay the recorded actions on the CPU oracle: same trajectory until the env stopped
+            n_act = int(np.argmax(np.all(tr[e, 1:] == tr[e, :-1], axis=1))) if np.any(np.all(tr[e, 1:] == tr[e, :-1], axis=1)) else 40
+            n_act = max(n_act, 1)
+            ref = orc.rollout_car(tr[e, 0, :6][None], tr[e, :n_act, 6:][None], r["goal_position"], grid)
+            k = min(n_act - 1, 39)
+            if k >= 1:
+                np.testing.assert_allclose(tr[e, 1:k + 1, :6], ref["traj"][0, :k], rtol=2e-3, atol=2e-3)
+            assert r["collision_count"][e] in (0.0, 1.0)
+            assert r["best_dist"][e] <= np.linalg.norm(tr[e, 0, :2] - r["goal_position"]) + 1e-6
+
+
+def test_online_scan_and_path_check(mazes):
+    from ditreeonlineplanner_b200.car_env import CarEnv
+    from ditreeonlineplanner_b200.online import check_no_obstacles_in_path, scan_and_update_maze
+    from ditreeonlineplanner_b200.planners.RRT import RRT_Planner
+    base = mazes["boxes"].astype(np.float64)
+    with_obs = base.copy()
+    with_obs[10:11, 15:19] = 1  # the reference's first inserted obstacle (row 10, col 15, 1 x 4)
+    env = CarEnv(maze_map=base.copy(), collision_checking=False)
+    start = np.array([*env.cell_rowcol_to_xy(np.array([12, 16])), np.pi / 2, 0, 0, 0])
+    goal = np.array([*env.cell_rowcol_to_xy(np.array([2, 17])), 0, 0, 0, 0])
+    pl = RRT_Planner(start, goal, env_id="carmaze", environment=env, sampler=None, action_horizon=8, local_map_size=20,
+                     local_map_scale=0.2, global_map_scale=1.0, time_budget=1)
+    pl.reset()
+    env.set_state(start.copy())
+    known = base.copy()
+    scanned = np.zeros_like(base)
+    np.random.seed(0)
+    scan_and_update_maze(pl, known, with_obs, scanned)
+    # oracle: same scan on the CPU
+    pose = np.array([start[0] + 10.0, 10.0 - start[1], start[2]])
+    d, e, v = orc.lidar_scan(pose, with_obs)
+    ee = np.floor(e).astype(int)
+    want_known = base.copy()
+    want_known[ee[:, 1], ee[:, 0]] = 1
+    assert np.array_equal(known, want_known) and np.array_equal(pl.maze, want_known)
+    want_scanned = np.zeros_like(base)
+    want_scanned[v[:, 1], v[:, 0]] = 2
+    want_scanned[ee[:, 1], ee[:, 0]] = 1
+    assert np.array_equal(scanned, want_scanned)
+    assert known[10, 16] == 1  # the inserted obstacle right ahead was discovered
+    # a straight path through the obstacle is flagged at the first point inside a scanned obstacle cell
+    path = np.stack([np.full(60, start[0]), np.linspace(start[1], start[1] + 6, 60)], 1)
+    got = check_no_obstacles_in_path(pl, scanned, path)
+    assert got == orc.path_first_obstacle(path, scanned) and got > 0
+    clear = np.tile(start[:2], (5, 1))
+    assert check_no_obstacles_in_path(pl, scanned, clear) == -1
+
+
+def test_mppi_controller_tracks_reference_path(mazes):
+    from ditreeonlineplanner_b200.mppi import MPPI
+    grid = mazes["boxes"]
+    ctl = MPPI(maze_data=grid.copy(), T=16, K=8192, nx=6, nu=2)
+    start = np.array([-7.5, -7.5, 0.0, 0.0, 0.0, 0.0])
+    goal = np.array([-2.5, -7.5, 0, 0, 0, 0])
+    ref = np.stack([np.linspace(-7.5, -2.5, 100), np.full(100, -7.5)], 1)
+    ctl.reset(start_state=start, goal_state=goal)
+    ctl.set_ref_path(ref)
+    torch.manual_seed(0)
+    state = start.copy()
+    d0 = np.linalg.norm(state[:2] - goal[:2])
+    for _ in range(60):
+        nxt, act, done = ctl.step(state)
+        assert act.shape == (2,) and done is not None
+        state = nxt
+        if done:
+            break
+    assert np.linalg.norm(state[:2] - goal[:2]) < d0 - 1.0  # moved along the corridor toward the goal
+    assert abs(state[1] + 7.5) < 0.6                          # and stayed on the reference line

@@ -468,7 +468,7 @@ def lidar_scan(pose, maze):
         dists.append(d)
         ends.append((pose[0] + d * np.cos(ang), pose[1] + d * np.sin(ang)))
         visited.extend(cells)
-    return np.array(dists), np.array(ends), np.array(visited).reshape(-1, 2)
+    return np.array(dists), np.array(ends), np.array(visited, dtype=int).reshape(-1, 2)
 
 
 def ray_probe(state, maze):

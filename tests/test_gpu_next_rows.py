@@ -49,7 +49,7 @@ def test_online_scan_and_path_check(mazes):
     with_obs = base.copy()
     with_obs[10:11, 15:19] = 1  # the reference's first inserted obstacle (row 10, col 15, 1 x 4)
     env = CarEnv(maze_map=base.copy(), collision_checking=False)
-    start = np.array([*env.cell_rowcol_to_xy(np.array([12, 16])), np.pi / 2, 0, 0, 0])
+    start = np.array([*env.cell_rowcol_to_xy(np.array([12, 15])), np.pi / 2, 0, 0, 0])
     goal = np.array([*env.cell_rowcol_to_xy(np.array([2, 17])), 0, 0, 0, 0])
     pl = RRT_Planner(start, goal, env_id="carmaze", environment=env, sampler=None, action_horizon=8, local_map_size=20,
                      local_map_scale=0.2, global_map_scale=1.0, time_budget=1)
@@ -70,7 +70,7 @@ def test_online_scan_and_path_check(mazes):
     want_scanned[v[:, 1], v[:, 0]] = 2
     want_scanned[ee[:, 1], ee[:, 0]] = 1
     assert np.array_equal(scanned, want_scanned)
-    assert known[10, 16] == 1  # the inserted obstacle right ahead was discovered
+    assert known[10, 15] == 1  # the inserted obstacle right ahead was discovered
     # a straight path through the obstacle is flagged at the first point inside a scanned obstacle cell
     path = np.stack([np.full(60, start[0]), np.linspace(start[1], start[1] + 6, 60)], 1)
     got = check_no_obstacles_in_path(pl, scanned, path)

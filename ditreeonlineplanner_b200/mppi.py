@@ -19,7 +19,7 @@ from .common.map_utils import _ctx_for
 
 
 class MPPI:
-    def __init__(self, maze_data, T=16, K=8192, nx=6, nu=2, lam=1.0, noise_sigma=(1.5, 0.8), lookahead=24,
+    def __init__(self, maze_data, T=16, K=8192, nx=6, nu=2, lam=0.02, noise_sigma=(1.5, 0.8), lookahead=24,
                  collision_cost=1.0e4, effort_cost=1.0e-3):
         self.maze = np.asarray(maze_data, dtype=np.float32)
         self.T, self.K, self.nx, self.nu = int(T), int(K), int(nx), int(nu)

@@ -91,7 +91,7 @@ def test_mppi_controller_tracks_reference_path(mazes):
     torch.manual_seed(0)
     state = start.copy()
     d0 = np.linalg.norm(state[:2] - goal[:2])
-    for _ in range(60):
+    for _ in range(120):
         nxt, act, done = ctl.step(state)
         assert act.shape == (2,) and done is not None
         state = nxt

@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--denoiser", default="large")
     ap.add_argument("--maze", default="boxes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-suite", action="store_true", help="skip the scenario-suite (scenarios/s) leg")
+    ap.add_argument("--suite-runs", type=int, default=8, help="runs per scenario in the suite leg (15 x runs units)")
     ap.add_argument("--prop-batch", type=int, default=1 << 20, help="candidates for the propagate+collide roofline leg")
     return ap.parse_args()
 
@@ -191,16 +193,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from ditreeonlineplanner_b200 import Context
+    from ditreeonlineplanner_b200 import get_context
     from ditreeonlineplanner_b200.expansion import TreeExpander
+    from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler
     from ditreeonlineplanner_b200.weights import UNET_DIMS, denoiser_flops, random_init
-    ctx = Context(local_rank)
+    ctx = get_context(local_rank)
     ctx.set_map(grid)
     dims = UNET_DIMS[args.denoiser]
     sd = random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims)
     B = args.batch
-    ctx.load_denoiser(sd, action_dim=2, horizon=64, cond_dim=7, emb_dim=400, map_size=20, down_dims=dims, max_batch=B)
-    del sd
+    # the reference-facing sampler object owns the packed weights (run_scenarios.py:179-185)
+    sampler = DiffusionSampler(sd, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2,
+                               obs_history=1, action_history=1, goal_conditioned=True, num_diffusion_iters=1,
+                               local_map_size=20, max_batch=B).eval()
+    assert sampler._context() is ctx
     exp = TreeExpander(ctx, meta, 20, 0.2, num_diffusion_iters=args.ode_steps, pred_horizon=64,
                        action_horizon=args.rollout)
     goal = goal_of(grid)
@@ -255,6 +261,29 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(t.item()) * 1e-3)
+
+    # ---------------- scenario suite, (scenario, run)-sharded over the ranks ----------------
+    suite = None
+    if not args.no_suite:
+        from ditreeonlineplanner_b200 import scenarios as sc
+        from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
+        invalidate_staged_map()
+        barrier()
+        t0 = time.perf_counter()
+        table, _ = sc.run_suite(sampler, total_runs=args.suite_runs, time_budget=1e9, rank=rank, world=world,
+                                device=ctx.device, planner_kwargs={"batch_size": 256, "iteration_cap": 256 * 8 * 2})
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rows_t = np.array(list(table.values()))
+        suite = {"units": len(table), "scenarios_per_s": len(table) / float(t.item()), "seconds": float(t.item()),
+                 "unit": "one (scenario, run) of test_scenarios_car: batched RRT, 256 candidates x 8 chunks x 2 rounds, "
+                         "K=1 (the reference's planning_diffusion_iters), large denoiser",
+                 "mean_tree_nodes": float(np.mean(rows_t[:, 6][rows_t[:, 6] > 0])) if (rows_t[:, 6] > 0).any() else 0.0,
+                 "gather": "one all_gather of [units/rank, 13] fp32 rows"}
+        ctx.set_map(grid)
+        invalidate_staged_map()
 
     # per-rank results gathered over NCCL (the only collective of this path: result rows)
     if world > 1:
@@ -323,7 +352,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "api": "TreeExpander.expand(states, prev_actions, goal) with NumPy host arrays"},
             "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges,
-            "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "clocks": clocks.summary()}
+            "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "suite": suite,
+            "clocks": clocks.summary()}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -179,7 +179,7 @@ class BatchedCarEnv:
     """B independent car environments on the device (the vectorised env the reference builds with
     SB3's DummyVecEnv in rollout_manager.py:612-664, without the per-env Python loop)."""
 
-    def __init__(self, maze_map, goals_xy, device=0):
+    def __init__(self, maze_map, goals_xy, device=None):
         self.maze = np.asarray(maze_map, dtype=np.float32)
         self.ctx = _ctx_for(self.maze, 1.0, device)
         self.goals = np.asarray(goals_xy, dtype=np.float32)

@@ -20,9 +20,10 @@ cc_calls = 0  # collision-check counter the reference's drivers reset and read (
 _staged = {}
 
 
-def _ctx_for(maze_map, scale=1.0, device=0):
+def _ctx_for(maze_map, scale=1.0, device=None):
     """Context with `maze_map` staged (re-uploaded only when the grid or its scale changed)."""
     ctx = get_context(device)
+    device = ctx.device.index
     g = np.ascontiguousarray(np.asarray(maze_map, dtype=np.float32))
     key = (g.shape, float(scale), g.tobytes())
     if _staged.get(device) != key:
@@ -31,8 +32,11 @@ def _ctx_for(maze_map, scale=1.0, device=0):
     return ctx
 
 
-def invalidate_staged_map(device=0):
-    _staged.pop(device, None)
+def invalidate_staged_map(device=None):
+    if device is None:
+        _staged.clear()
+    else:
+        _staged.pop(device, None)
 
 
 def create_local_map(global_map, x, y, theta, map_size, scale, s_global, map_center):

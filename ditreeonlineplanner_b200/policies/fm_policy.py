@@ -57,12 +57,16 @@ class DiffusionSampler(nn.Module):
     # nn.Module.to()/eval() keep working; the packed weights live in the device context
     def _context(self):
         if self._ctx is None:
-            ctx = get_context(0)
+            ctx = get_context()
             dims, emb, cond_dim, A = _infer_cfg(self._state_dict)
             if A != self.action_dim:
                 raise ValueError(f"action_dim {self.action_dim} does not match the network ({A})")
-            ctx.load_denoiser(self._state_dict, action_dim=A, horizon=self.pred_horizon, cond_dim=cond_dim, emb_dim=emb,
-                              map_size=int(self.local_map_size), down_dims=dims, max_batch=self._max_batch)
+            key = (id(self._state_dict), self.pred_horizon, int(self.local_map_size), self._max_batch)
+            if getattr(ctx, "_loaded_key", None) != key:  # several samplers may share one set of weights
+                ctx.load_denoiser(self._state_dict, action_dim=A, horizon=self.pred_horizon, cond_dim=cond_dim,
+                                  emb_dim=emb, map_size=int(self.local_map_size), down_dims=dims,
+                                  max_batch=self._max_batch)
+                ctx._loaded_key = key
             self._ctx = ctx
         return self._ctx
 

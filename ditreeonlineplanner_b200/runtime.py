@@ -326,8 +326,14 @@ class Context:
 _default = {}
 
 
-def get_context(device=0):
-    """Process-wide context per device (the reference's modules are process-wide singletons too)."""
+def get_context(device=None):
+    """Process-wide context per device (the reference's modules are process-wide singletons too).
+    ``device=None`` means torch's current CUDA device, so one-process-per-GPU launches (torchrun sets
+    the device from LOCAL_RANK) get the context of their own GPU."""
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ditreeonlineplanner_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        device = torch.cuda.current_device()
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)
     if idx not in _default:
         _default[idx] = Context(idx)

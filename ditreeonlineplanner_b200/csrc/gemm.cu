@@ -228,8 +228,8 @@ struct SmemPlan {
   static constexpr int kStages = (192 * 1024 / kStage) > 8 ? 8 : (192 * 1024 / kStage);
   static constexpr int kParamFloats = 5 * BN;                  // bias, gamma, beta, film_t scale, film_t shift
   static constexpr int kRedFloats = (4 * EPI_SPLIT) * 8 * 8 * 2;  // [warp][segment][group][sum,sq]
-  static constexpr int kFilmSamples = 8;                       // FiLM rows staged per tile (tiles of >= 16-row samples)
-  static constexpr int kFilmFloats = kFilmSamples * 2 * BN;    // [sample][scale | shift][BN], per-step part pre-added
+  static constexpr int kFilmSamples = 4;                       // tiles holding <= 4 samples (T >= 32) stage FiLM + GN coefficients
+  static constexpr int kFilmFloats = 2 * kFilmSamples * 2 * BN;  // FiLM [sample][scale | shift][BN] + GN affine [sample][A | B][BN]
   static constexpr int kBytes =
       kStages * kStage + (kParamFloats + kRedFloats + kFilmFloats) * 4 + 256 /*barriers*/ + 1024 /*align*/;
 };
@@ -254,6 +254,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   float* s_par = reinterpret_cast<float*>(base_ptr + P::kStages * P::kStage);
   float* s_red = s_par + P::kParamFloats;
   float* s_film = s_red + P::kRedFloats;
+  float* s_coef = s_film + P::kFilmSamples * 2 * BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_film + P::kFilmFloats);
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base word
   const uint32_t bar_full = dt_smem_u32(bars);
@@ -411,6 +412,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     const int ns = g.tiles_per_sample > 0 ? 1 : g.nb;  // samples per tile
     const bool film_smem = (EPI == EPI_GN_MISH) && g.film && ns <= P::kFilmSamples;
     constexpr int PF = (P::kFilmSamples * 2 * BN + NET - 1) / NET;  // FiLM values staged per thread (at most)
+    static_assert(NG <= 8, "red[] holds 8 groups per warp");
     float pf_par[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     float pf_film[PF];
     auto prefetch = [&](int tile_) {
@@ -479,78 +481,103 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off;
       const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
 
-      float mean[NG], rstd[NG];
+      // GroupNorm groups seen by this warp's column slice: NLG whole groups when a group fits in the
+      // slice, otherwise the slice is part of ONE group that spans SPG slices.
+      constexpr int NLG = (GW <= HALF) ? HALF / GW : 1;
+      constexpr int SPG = (GW <= HALF) ? 1 : GW / HALF;
+      float mean[NLG], rstd[NLG];
       uint32_t rb[2][CH];
+      const int smp_in_tile = g.tiles_per_sample > 0 ? 0 : row / g.T;
       if (EPI == EPI_GN_MISH) {
-        float gs[NG], gq[NG];
+        float gs[NLG], gq[NLG];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) gs[i] = gq[i] = 0.f;
-        // pass 1: per-row partial sums of (acc + bias) and its square for the groups in this half
+        for (int i = 0; i < NLG; ++i) gs[i] = gq[i] = 0.f;
+        // pass 1: per-row partial sums of (acc + bias) and its square for the groups of this slice
         tmem_ld16(taddr, rb[0]);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           tmem_wait(rb[c & 1]);
           if (c + 1 < NCH) tmem_ld16(taddr + (c + 1) * CH, rb[(c + 1) & 1]);
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const float v = __uint_as_float(rb[c & 1][j]) + sp[c * CH + j];
-            // column (half * HALF + c * CH + j): its group index is compile-time per slice, `half` is warp-uniform
+          for (int j = 0; j < CH; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(sp + c * CH + j);
+            const float bia[4] = {bi.x, bi.y, bi.z, bi.w};
 #pragma unroll
-            for (int h = 0; h < EPI_SPLIT; ++h) {
-              if (half == h) {
-                gs[(h * HALF + c * CH + j) / GW] += v;
-                gq[(h * HALF + c * CH + j) / GW] += v * v;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float v = __uint_as_float(rb[c & 1][j + e]) + bia[e];
+              gs[(GW <= HALF) ? (c * CH + j + e) / GW : 0] += v;
+              gq[(GW <= HALF) ? (c * CH + j + e) / GW : 0] += v * v;
             }
           }
         }
         // reduce over the rows of this sample held by this warp (segments of min(T,32) lanes) ...
         const int span = g.T < 32 ? g.T : 32;
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
+        for (int i = 0; i < NLG; ++i) {
           for (int off = 1; off < span; off <<= 1) {
             gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], off);
             gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
           }
         }
-        // ... then across warps through shared memory: the partner half always, other quarters when T > 32
-        float* red = s_red;  // reuse across tiles is ordered by the two barriers at the top of the tile loop
+        // ... then across warps through shared memory: other lane quarters when a sample spans several
+        // warps (T > 32), other column slices when a group spans several slices (GW > HALF)
+        float* red = s_red;  // [warp][segment][local group][sum, sq]; reuse across tiles is ordered by the top barriers
         const int seg = lane / span;
         if ((lane % span) == 0) {
 #pragma unroll
-          for (int i = 0; i < NG; ++i) {
+          for (int i = 0; i < NLG; ++i) {
             red[((ew * 8 + seg) * 8 + i) * 2 + 0] = gs[i];
             red[((ew * 8 + seg) * 8 + i) * 2 + 1] = gq[i];
           }
         }
         epi_bar_sync();
-        const int rows_s = g.T > BM ? BM : g.T;       // rows of one sample inside this tile
+        const int rows_s = g.T > BM ? BM : g.T;         // rows of one sample inside this tile
         const int wps = rows_s > 32 ? rows_s / 32 : 1;  // lane quarters per sample
         const int q0 = (q / wps) * wps;
+        const int h0 = (half / SPG) * SPG;
+        const float inv_n = 1.0f / (float)(rows_s * GW);
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          float a = 0.f, c = 0.f;
+        for (int i = 0; i < NLG; ++i) {
+          float sa = 0.f, sq = 0.f;
           for (int qq = q0; qq < q0 + wps; ++qq) {
 #pragma unroll
-            for (int hh = 0; hh < EPI_SPLIT; ++hh) {
-              const int w2 = ((qq + 2) & 3) + 4 * hh;  // ew of the warp with lane quarter qq, column slice hh
-              a += red[((w2 * 8 + seg) * 8 + i) * 2 + 0];
-              c += red[((w2 * 8 + seg) * 8 + i) * 2 + 1];
+            for (int hh = 0; hh < SPG; ++hh) {
+              const int w2 = ((qq + 2) & 3) + 4 * (h0 + hh);  // ew of the warp with lane quarter qq, column slice h0+hh
+              sa += red[((w2 * 8 + seg) * 8 + i) * 2 + 0];
+              sq += red[((w2 * 8 + seg) * 8 + i) * 2 + 1];
             }
           }
-          const float inv_n = 1.0f / (float)(rows_s * GW);
-          mean[i] = a * inv_n;
-          const float var = fmaxf(c * inv_n - mean[i] * mean[i], 0.f);
+          mean[i] = sa * inv_n;
+          const float var = fmaxf(sq * inv_n - mean[i] * mean[i], 0.f);
           rstd[i] = rsqrtf(var + 1e-5f);
         }
       }
 
-      // pass 2: normalise / activate / modulate and store this warp's half of the columns
+      // Per-(sample, column) affine of the normalisation, shared by the rows of a sample:
+      //   t = ((acc + bias) - mean) * rstd * gamma + beta = acc * A + B
+      // computed once per tile into shared memory when a tile holds few samples (coef_smem).
+      const bool coef_smem = (EPI == EPI_GN_MISH) && ns <= P::kFilmSamples;
+      if (coef_smem) {
+        const int rows_s = g.T > BM ? BM : g.T;
+        const int idx = (g.tiles_per_sample > 0 ? row : row % g.T);  // this thread's rank among the rows of its sample
+        for (int cl = idx; cl < HALF; cl += rows_s) {
+          const float m_ = pick<NLG>(mean, (GW <= HALF) ? cl / GW : 0);
+          const float r_ = pick<NLG>(rstd, (GW <= HALF) ? cl / GW : 0);
+          const float A = r_ * sp[BN + cl];
+          s_coef[(smp_in_tile * 2 + 0) * BN + half * HALF + cl] = A;
+          s_coef[(smp_in_tile * 2 + 1) * BN + half * HALF + cl] = (sp[cl] - m_) * A + sp[2 * BN + cl];
+        }
+        epi_bar_sync();
+      }
+
+      // pass 2: normalise / activate / modulate and store this warp's slice of the columns
       const int nh = n0 + half * HALF;
       const float* film_row = (EPI == EPI_GN_MISH && g.film && valid && !film_smem) ? g.film + b * g.film_ld + nh : nullptr;
-      const int smp_in_tile = g.tiles_per_sample > 0 ? 0 : row / g.T;
-      const float* fs = s_film + smp_in_tile * 2 * BN + half * HALF;  // staged scale row; shift row at + BN
+      const float* fs = s_film + smp_in_tile * 2 * BN + half * HALF;  // staged FiLM scale row; shift row at + BN
+      const float* cf = s_coef + smp_in_tile * 2 * BN + half * HALF;  // staged A row; B row at + BN
       const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + nh : nullptr;
+      __nv_bfloat16* out_b = g.out_bf16 ? g.out_bf16 + out_row * g.ldc + nh : nullptr;
+      float* out_f = g.out_f32 ? g.out_f32 + out_row * g.ldc + nh : nullptr;
       uint4 res_next[2];
       if (res_row) {
         res_next[0] = __ldg(reinterpret_cast<const uint4*>(res_row));
@@ -574,26 +601,30 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         const uint32_t* r = rb[c & 1];
         float y[CH];
         if (EPI == EPI_GN_MISH) {
-          // groups touched by this chunk: one when GW >= 16, else 16 / GW
-          constexpr int GPC = (GW >= CH) ? 1 : CH / GW;
-          float cm[GPC], cr[GPC];
+          if (coef_smem) {
 #pragma unroll
-          for (int u = 0; u < GPC; ++u) {
-            cm[u] = pick<NG>(mean, (half * HALF + c0) / GW + u);
-            cr[u] = pick<NG>(rstd, (half * HALF + c0) / GW + u);
-          }
+            for (int j = 0; j < CH; j += 4) {
+              const float4 A4 = *reinterpret_cast<const float4*>(cf + c0 + j);
+              const float4 B4 = *reinterpret_cast<const float4*>(cf + BN + c0 + j);
+              y[j + 0] = mish_f(fmaf(__uint_as_float(r[j + 0]), A4.x, B4.x));
+              y[j + 1] = mish_f(fmaf(__uint_as_float(r[j + 1]), A4.y, B4.y));
+              y[j + 2] = mish_f(fmaf(__uint_as_float(r[j + 2]), A4.z, B4.z));
+              y[j + 3] = mish_f(fmaf(__uint_as_float(r[j + 3]), A4.w, B4.w));
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
-            const float4 ga = *reinterpret_cast<const float4*>(sp + BN + c0 + j);
-            const float4 be = *reinterpret_cast<const float4*>(sp + 2 * BN + c0 + j);
-            const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, gam[4] = {ga.x, ga.y, ga.z, ga.w},
-                        bet[4] = {be.x, be.y, be.z, be.w};
+            for (int j = 0; j < CH; j += 4) {
+              const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
+              const float4 ga = *reinterpret_cast<const float4*>(sp + BN + c0 + j);
+              const float4 be = *reinterpret_cast<const float4*>(sp + 2 * BN + c0 + j);
+              const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, gam[4] = {ga.x, ga.y, ga.z, ga.w},
+                          bet[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int u = (GW >= CH) ? 0 : (j + e) / GW;
-              const float v = __uint_as_float(r[j + e]) + bia[e];
-              y[j + e] = mish_f((v - cm[u]) * cr[u] * gam[e] + bet[e]);
+              for (int e = 0; e < 4; ++e) {
+                const int u = (GW <= HALF) ? (c0 + j + e) / GW : 0;
+                const float v = __uint_as_float(r[j + e]) + bia[e];
+                y[j + e] = mish_f((v - mean[u]) * rstd[u] * gam[e] + bet[e]);
+              }
             }
           }
           if (film_smem) {
@@ -601,10 +632,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             for (int j = 0; j < CH; j += 4) {
               const float4 sc = *reinterpret_cast<const float4*>(fs + c0 + j);
               const float4 sh = *reinterpret_cast<const float4*>(fs + BN + c0 + j);
-              y[j + 0] = y[j + 0] * sc.x + sh.x;
-              y[j + 1] = y[j + 1] * sc.y + sh.y;
-              y[j + 2] = y[j + 2] * sc.z + sh.z;
-              y[j + 3] = y[j + 3] * sc.w + sh.w;
+              y[j + 0] = fmaf(y[j + 0], sc.x, sh.x);
+              y[j + 1] = fmaf(y[j + 1], sc.y, sh.y);
+              y[j + 2] = fmaf(y[j + 2], sc.z, sh.z);
+              y[j + 3] = fmaf(y[j + 3], sc.w, sh.w);
             }
           } else if (film_row) {
 #pragma unroll
@@ -621,18 +652,23 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) y[j] = __uint_as_float(r[j]) + sp[c0 + j];
+          for (int j = 0; j < CH; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
+            y[j + 0] = __uint_as_float(r[j + 0]) + bi.x;
+            y[j + 1] = __uint_as_float(r[j + 1]) + bi.y;
+            y[j + 2] = __uint_as_float(r[j + 2]) + bi.z;
+            y[j + 3] = __uint_as_float(r[j + 3]) + bi.w;
+          }
         }
         if (res_row) {
 #pragma unroll
           for (int j = 0; j < CH; j += 8) {
             const uint4 pk = res_cur[j / 8];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 f = __bfloat1622float2(h2[u]);
-              y[j + 2 * u] += f.x;
-              y[j + 2 * u + 1] += f.y;
+            for (int u = 0; u < 4; ++u) {  // bf16 -> fp32 is a 16-bit shift
+              y[j + 2 * u] += __uint_as_float(w4[u] << 16);
+              y[j + 2 * u + 1] += __uint_as_float(w4[u] & 0xFFFF0000u);
             }
           }
         }
@@ -641,21 +677,20 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           for (int j = 0; j < CH; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (valid) {
-          if (g.out_bf16) {
-            __nv_bfloat16* o = g.out_bf16 + out_row * g.ldc + nh + c0;
+          if (out_b) {
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               uint4 pk;
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
               for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(y[j + 2 * u], y[j + 2 * u + 1]);
-              *reinterpret_cast<uint4*>(o + j) = pk;
+              *reinterpret_cast<uint4*>(out_b + c0 + j) = pk;
             }
           }
-          if (g.out_f32) {
-            float* o = g.out_f32 + out_row * g.ldc + nh + c0;
+          if (out_f) {
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            for (int j = 0; j < CH; j += 4)
+              *reinterpret_cast<float4*>(out_f + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
         }
       }

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Secondary configurations of BASELINE.json (configs[3], configs[4]), CUDA-event timed:
+  C4  lidar_2d_sim ray-marching (181 rays / pose) and one MPPI control tick with K = 8192 rollouts
+  C5  antmaze: local map + conditioning + FM sampling (large net, K = 1) + collision, B = 16384
+Prints one JSON object; the committed copy lives in profiles/."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ditreeonlineplanner_b200 import get_context, load_maze, load_metadata  # noqa: E402
+from ditreeonlineplanner_b200.weights import UNET_DIMS, denoiser_flops, random_init  # noqa: E402
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+out = {}
+ctx = get_context(0)
+rng = np.random.default_rng(0)
+
+# ---------------- C4: lidar + MPPI ----------------
+boxes = load_maze("boxes").astype(np.float32)
+ctx.set_map(boxes)
+P = 4096
+free = np.argwhere(boxes == 0)
+cells = free[rng.integers(0, len(free), P)]
+poses = torch.as_tensor(np.stack([cells[:, 1] + rng.uniform(0.2, 0.8, P), cells[:, 0] + rng.uniform(0.2, 0.8, P),
+                                  rng.uniform(-3, 3, P)], 1).astype(np.float32)).cuda()
+ms = timed(lambda: ctx.lidar_scan(poses))
+out["C4_lidar"] = {"poses": P, "rays": P * 181, "ms": ms, "rays_per_s": P * 181 / ms * 1e3,
+                   "reference_cpu_rays_per_s": 5.6e3, "note": "reference figure: SURVEY section 6 (32.6 ms / scan)"}
+from ditreeonlineplanner_b200.mppi import MPPI  # noqa: E402
+ctl = MPPI(maze_data=boxes.copy(), T=16, K=8192, nx=6, nu=2)
+ctl.reset(start_state=np.array([-7.5, -7.5, 0, 1.0, 0.3, 0]), goal_state=np.array([-2.5, -7.5, 0, 0, 0, 0]))
+ctl.set_ref_path(np.stack([np.linspace(-7.5, -2.5, 100), np.full(100, -7.5)], 1))
+state = np.array([-7.5, -7.5, 0, 1.0, 0.3, 0])
+noise = torch.randn((8192, 16, 2), device="cuda")
+
+
+def mppi_device_part():
+    cost, _ = ctl.rollout_costs(state, noise)
+    ctx.mppi_reduce(cost, noise, 0.02, ctl.u)
+
+
+ms = timed(mppi_device_part, reps=50)
+out["C4_mppi"] = {"K": 8192, "T": 16, "ms_per_tick_device": ms, "rollouts_per_s": 8192 / ms * 1e3,
+                  "reference_ticks_per_s": 10.8, "note": "rollout (propagate+collide kernel) + cost + dt_mppi_reduce; "
+                  "reference figure from TotalFinal.csv (MPPI K=10,T=16): 10.8 control steps / s"}
+
+# ---------------- C5: antmaze ----------------
+huge = load_maze("random_huge").astype(np.float32)
+ctx.set_map(huge, 4.0)
+meta = load_metadata("antmaze")
+B = 16384
+dims = UNET_DIMS["large"]
+ctx.load_denoiser(random_init(seed=0, input_dim=8, cond_dim=97, emb_dim=400, down_dims=dims), action_dim=8, horizon=16,
+                  cond_dim=97, emb_dim=400, map_size=16, down_dims=dims, max_batch=B)
+free = np.argwhere(huge == 0)
+cells = free[rng.integers(0, len(free), B)]
+st = np.zeros((B, 3, 29), np.float32)
+st[..., 0] = ((cells[:, 1] + 0.5) * 4 - 62)[:, None]
+st[..., 1] = (62 - (cells[:, 0] + 0.5) * 4)[:, None]
+st[..., 2:] = (meta["Observations_mean"] + meta["Observations_std"] * rng.normal(size=(B, 3, 27))).astype(np.float32)
+obs = torch.as_tensor(st).cuda()
+prev = torch.as_tensor((meta["Actions_mean"] + meta["Actions_std"] * rng.normal(size=(B, 8))).astype(np.float32)).cuda()
+goal = torch.tensor([10.0, -20.0], device="cuda")
+noise = torch.randn((B, 16, 8), device="cuda")
+last = obs[:, -1, :].contiguous()
+pose = torch.cat([last[:, :2], torch.zeros((B, 1), device="cuda")], 1)  # rollout() uses yaw = 0 for the ant
+
+
+def ant_pass():
+    lm = ctx.local_map(pose, 16, 0.8, bf16_signed=True)
+    cond = ctx.build_cond_ant(obs, prev, goal, meta, 3, 16.0)
+    act = ctx.fm_sample(noise, cond, lm, 1, meta["Actions_mean"], meta["Actions_std"])
+    flags = ctx.collide_ant(last, 1.2)
+    return act, flags
+
+
+ms = timed(ant_pass, reps=5)
+ctx.profile_begin()
+ant_pass()
+gemm_ms, n = ctx.profile_end()
+enc, unet = denoiser_flops(1, input_dim=8, cond_dim=97, horizon=16, map_size=16, down_dims=dims)
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+out["C5_ant"] = {"B": B, "ms": ms, "candidates_per_s": B / ms * 1e3, "gemm_ms": gemm_ms, "gemm_launches": n,
+                 "gemm_tflops": B * (enc + unet) / (gemm_ms * 1e-3) / 1e12,
+                 "frac_of_measured_sustained_bf16_peak": B * (enc + unet) / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                 "algorithmic_gflop_per_candidate": (enc + unet) / 1e9,
+                 "tensor_bound_candidates_per_s": peaks["bf16_tflops_sustained"] * 1e12 / (enc + unet)}
+print(json.dumps(out, indent=1))

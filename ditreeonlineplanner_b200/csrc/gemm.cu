@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
@@ -102,12 +105,14 @@ __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// arrive on the copy of `bar` that lives in CTA `rank` of the cluster
+// arrive on the copy of `bar` that lives in CTA `rank` of the cluster.  Relaxed: the arrival only hands
+// TMEM back to the MMA warp (ordered by tcgen05.fence::before_thread_sync); a release would make the
+// warp wait for all its outstanding global stores to drain (MEMBAR + ERRBAR) once per tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(rank)
       : "memory");
 }
@@ -588,7 +593,18 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       for (int c = 0; c < NCH; ++c) {
         const int c0 = c * CH;
         tmem_wait(rb[c & 1]);
-        if (c + 1 < NCH) tmem_ld16(taddr + c0 + CH, rb[(c + 1) & 1]);
+        if (c + 1 < NCH) {
+          tmem_ld16(taddr + c0 + CH, rb[(c + 1) & 1]);
+        } else {
+          // the last TMEM read of this tile has landed in registers: hand the accumulator back to the
+          // (leader's) MMA warp now, one elected arrival per warp, and finish the math / stores afterwards
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+            else mbar_arrive_relaxed(bar_tempty + 8 * acc);
+          }
+        }
         uint4 res_cur[2];
         if (res_row) {  // software pipeline: this chunk's residual was requested one iteration ago
           res_cur[0] = res_next[0];
@@ -693,13 +709,6 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
               *reinterpret_cast<float4*>(out_f + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
         }
-      }
-      // release the accumulator to the (leader's) MMA warp: one elected arrival per warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-        else mbar_arrive(bar_tempty + 8 * acc);
       }
       if (++acc == 2) {
         acc = 0;

@@ -238,6 +238,8 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     gemm_ms, gemm_launches = ctx.profile_end()
+    prof_csv = os.path.join("/tmp", f"ditree_gemm_launches_rank{rank}.csv")
+    ctx.profile_csv(prof_csv)
     launches = ctx.launches - launches0
     clocks.stop_flag = True
     clocks.join(timeout=2)
@@ -307,10 +309,40 @@ def main():
     flops_step = B * (enc_f + args.ode_steps * unet_f)
     achieved = flops_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    # the single heaviest instance of the family: its launches' average CUDA-event duration, measured above,
+    # and the DRAM traffic of one such launch from the committed ncu capture
+    dominant = None
+    try:
+        import csv as _csv
+        recs = list(_csv.DictReader(open(prof_csv)))
+        byshape = {}
+        for r_ in recs:
+            key = (int(r_["M"]), int(r_["N"]), int(r_["K"]), int(r_["epi"]))
+            byshape.setdefault(key, []).append(float(r_["ms"]))
+        key = max(byshape, key=lambda k_: sum(byshape[k_]))
+        avg_ms = sum(byshape[key]) / len(byshape[key])
+        fl = 2.0 * key[0] * key[1] * key[2]
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("flop") == fl:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        dominant = {"shape_M_N_K": list(key[:3]), "epilogue": "GroupNorm+Mish(+FiLM/residual)" if key[3] else "bias",
+                    "launches_in_timed_region": len(byshape[key]), "avg_launch_ms": avg_ms,
+                    "share_of_gemm_time": sum(byshape[key]) / gemm_ms, "achieved": fl / (avg_ms * 1e-3) / 1e12,
+                    "frac": fl / (avg_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0),
+                    "traffic": traffic, "algorithmic_bytes": 2 * (2 * key[0] * key[1]) + 2 * key[1] * key[2]
+                    if key[1] == key[2] // 3 else None}
+    except Exception as ex:  # the per-launch breakdown is auxiliary
+        dominant = {"error": str(ex)}
     roofline = {"kernel": "k_conv_gemm (tcgen05 implicit-GEMM conv + fused GN/Mish/FiLM epilogue)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
-                "traffic": None, "gemm_ms_per_step": gemm_ms / args.steps, "gemm_launches_per_step": gemm_launches / args.steps,
+                "traffic": dominant.get("traffic") if isinstance(dominant, dict) else None,
+                "traffic_note": "DRAM bytes (read+write) of ONE launch of the dominant instance, ncu --set full "
+                                "(profiles/r01_ncu_gemm_gn256_cg2.md); compare with dominant_instance.algorithmic_bytes",
+                "dominant_instance": dominant, "gemm_ms_per_step": gemm_ms / args.steps, "gemm_launches_per_step": gemm_launches / args.steps,
                 "gemm_share_of_step": gemm_ms / args.steps / ms_step,
                 "algorithmic_gflop_per_candidate": (enc_f + args.ode_steps * unet_f) / 1e9}
 

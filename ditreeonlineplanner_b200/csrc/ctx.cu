@@ -38,6 +38,7 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   dt_denoiser_free(ctx);
   if (ctx->d_map) cudaFree(ctx->d_map);
+  if (ctx->d_qmap) cudaFree(ctx->d_qmap);
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -121,16 +122,70 @@ extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int col
   const int padded = ((rows * cols + 15) / 16) * 16;
   std::vector<uint8_t> bytes(padded, 0);
   for (int i = 0; i < rows * cols; ++i) bytes[i] = (grid_host[i] == 1.0f) ? 1 : (grid_host[i] != 0.0f ? 2 : 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (padded > ctx->map_bytes || !ctx->d_map) {
-    DT_CUDA(cudaStreamSynchronize(st));
-    if (ctx->d_map) DT_CUDA(cudaFree(ctx->d_map));
-    ctx->d_map = nullptr;
-    DT_CUDA(cudaMalloc(&ctx->d_map, padded));
+  // Quadrant table of the car collision fast path (carfast.cuh).  The grid is padded by DT_QPAD rings of
+  // "always collides" cells (a ball centre outside the grid collides, common/map_utils.py:255-259) and the
+  // table is indexed by the grid VERTEX (k, j) nearest to the ball centre; each entry holds four nibbles, one
+  // per cell quadrant touching that vertex: nibble (a, b) at bit 8a + 4b describes the cell above (a = 1) /
+  // below (a = 0) and left (b = 1) / right (b = 0) of the vertex, i.e. the ball sits in the lower (a = 1) /
+  // upper half and right (b = 1) / left half of that cell:
+  //   bit 0  the side neighbour in x on that half is a wall   (index clipped as map_utils.py:281-296)
+  //   bit 1  the side neighbour in y on that half is a wall
+  //   bit 2  the diagonal neighbour of that quadrant is a wall (row clipped with R-1, column with R-1: sic, :326)
+  //   bit 3  collides wherever the ball is: padding cell, own cell is a wall, or any of the four diagonal
+  //          cells lies outside the grid (`invalid_cell`, :322-327, which makes every border cell collide)
+  // Built only when rows <= cols: on taller maps the row-count clip can index past the last column (NumPy
+  // raises IndexError) and the exact code, which reports that, is used instead.
+  std::vector<uint16_t> q;
+  int qpadded = 0;
+  if (rows <= cols) {
+    const int VR = rows + 2 * DT_QPAD + 1, VC = cols + 2 * DT_QPAD + 1;
+    qpadded = ((VR * VC * 2 + 15) / 16) * 16;
+    q.assign(qpadded / 2, 0x8888);
+    auto wall = [&](int r, int c) { return bytes[r * cols + c] == 1; };
+    auto clip = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    for (int k = 0; k < VR; ++k)
+      for (int j = 0; j < VC; ++j) {
+        unsigned e = 0;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int r = k - a - DT_QPAD, c = j - b - DT_QPAD;  // the cell of this quadrant, grid indices
+            unsigned nib = 8u;
+            if (r >= 0 && r < rows && c >= 0 && c < cols) {
+              const bool border = (r == 0) | (r == rows - 1) | (c == 0) | (c == cols - 1);  // a diagonal is outside
+              nib = (wall(r, c) || border) ? 8u : 0u;
+              const int sx = b ? 1 : -1, sy = a ? 1 : -1;
+              nib |= wall(r, clip(c + sx, 0, cols - 1)) ? 1u : 0u;
+              nib |= wall(clip(r + sy, 0, rows - 1), c) ? 2u : 0u;
+              nib |= wall(clip(r + sy, 0, rows - 1), clip(c + sx, 0, rows - 1)) ? 4u : 0u;  // sic: rows - 1
+            }
+            e |= nib << (8 * a + 4 * b);
+          }
+        q[k * VC + j] = (uint16_t)e;
+      }
   }
-  // synchronous: the staging vector dies at return, and the reference's update_maze is synchronous too
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((size_t)padded > ctx->map_capacity || (size_t)qpadded > ctx->qmap_capacity) {
+    DT_CUDA(cudaStreamSynchronize(st));
+    if ((size_t)padded > ctx->map_capacity) {
+      if (ctx->d_map) DT_CUDA(cudaFree(ctx->d_map));
+      ctx->d_map = nullptr;
+      ctx->map_capacity = 0;
+      DT_CUDA(cudaMalloc(&ctx->d_map, padded));
+      ctx->map_capacity = padded;
+    }
+    if ((size_t)qpadded > ctx->qmap_capacity) {
+      if (ctx->d_qmap) DT_CUDA(cudaFree(ctx->d_qmap));
+      ctx->d_qmap = nullptr;
+      ctx->qmap_capacity = 0;
+      DT_CUDA(cudaMalloc(&ctx->d_qmap, qpadded));
+      ctx->qmap_capacity = qpadded;
+    }
+  }
+  // synchronous: the staging vectors die at return, and the reference's update_maze is synchronous too
   DT_CUDA(cudaMemcpyAsync(ctx->d_map, bytes.data(), padded, cudaMemcpyHostToDevice, st));
+  if (qpadded) DT_CUDA(cudaMemcpyAsync(ctx->d_qmap, q.data(), qpadded, cudaMemcpyHostToDevice, st));
   DT_CUDA(cudaStreamSynchronize(st));
+  ctx->qmap_bytes = qpadded;
   ctx->rows = rows;
   ctx->cols = cols;
   ctx->s_global = (double)s_global;

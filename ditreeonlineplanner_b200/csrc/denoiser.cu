@@ -142,6 +142,57 @@ k_final_euler(const __nv_bfloat16* __restrict__ f, int64_t rows, int C0, int A, 
   }
 }
 
+// Specialisation for A = 2 (car): each lane keeps the weights of its channels in registers, so a
+// row costs NI coalesced 4-byte loads and 4*NI FMAs (the generic kernel re-reads the weights per row).
+template <int NI>  // C0 = 64 * NI
+__global__ void __launch_bounds__(256)
+k_final_euler_a2(const __nv_bfloat16* __restrict__ f, int64_t rows, const float* __restrict__ w,
+                 const float* __restrict__ bias, float dt, float* __restrict__ a, float* __restrict__ vel_out,
+                 const float* __restrict__ norm) {
+  constexpr int C0 = 64 * NI;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float w0[NI][2], w1[NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = lane * 2 + 64 * i;
+    w0[i][0] = w[c]; w0[i][1] = w[c + 1];
+    w1[i][0] = w[C0 + c]; w1[i][1] = w[C0 + c + 1];
+  }
+  const float b0 = bias[0], b1 = bias[1];
+  for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
+    const __nv_bfloat16* row = f + r * C0;
+    float2 v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + lane * 2 + 64 * i));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      s0 += v[i].x * w0[i][0] + v[i].y * w0[i][1];
+      s1 += v[i].x * w1[i][0] + v[i].y * w1[i][1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (lane < 2) {
+      float vv = (lane == 0 ? s0 + b0 : s1 + b1);
+      if (vel_out) {
+        vel_out[r * 2 + lane] = vv;
+      } else {
+        float st = a[r * 2 + lane] + vv * dt;
+        if (norm) st = st * norm[2 + lane] + norm[lane];
+        a[r * 2 + lane] = st;
+      }
+    }
+  }
+}
+
+static int launch_final_euler(dt_ctx* ctx, const __nv_bfloat16* f, int64_t rows, int C0, int A, const float* w,
+                              const float* bias, float dt, float* a, float* vel_out, const float* norm,
+                              cudaStream_t st);
+
 // Mish([emb | cond]) as the bf16 A operand of the per-candidate FiLM GEMM, zero padded to kc_pad
 __global__ void k_film_input(const float* __restrict__ emb, int emb_ld, int E, const float* __restrict__ cond, int G,
                              int64_t B, int kc_pad, __nv_bfloat16* __restrict__ out) {
@@ -686,6 +737,18 @@ static inline int ew_grid(int64_t n, const dt_ctx* ctx) {
   return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
+static int launch_final_euler(dt_ctx* ctx, const __nv_bfloat16* f, int64_t rows, int C0, int A, const float* w,
+                              const float* bias, float dt, float* a, float* vel_out, const float* norm,
+                              cudaStream_t st) {
+  const int grid = ew_grid(rows * 32, ctx);
+  if (A == 2 && C0 == 512) k_final_euler_a2<8><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
+  else if (A == 2 && C0 == 256) k_final_euler_a2<4><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
+  else if (A == 2 && C0 == 64) k_final_euler_a2<1><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
+  else k_final_euler<<<grid, 256, 0, st>>>(f, rows, C0, A, w, bias, dt, a, vel_out, norm);
+  DT_LAUNCH_CHECK("k_final_euler");
+  return DT_OK;
+}
+
 // conv1d k=3 (or k=1) stride 1 over one or two (channel-concatenated) sources
 static int conv_s1(dt_ctx* ctx, const ConvW& w, int k, Act in0, const Act* in1, int64_t B, ConvGemm g,
                    cudaStream_t st) {
@@ -1013,9 +1076,9 @@ extern "C" int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* em
     k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(sample + b0 * d->T * d->A, rows, d->A, d->X);
     DT_LAUNCH_CHECK("k_prep_sample");
     if ((rc = unet_body(ctx, d, nb, d->film_time, st))) return rc;
-    k_final_euler<<<ew_grid(rows * 32, ctx), 256, 0, st>>>(d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, 0.f,
-                                                           nullptr, vel_out + b0 * d->T * d->A, nullptr);
-    DT_LAUNCH_CHECK("k_final_euler");
+    if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, 0.f, nullptr,
+                                 vel_out + b0 * d->T * d->A, nullptr, st)))
+      return rc;
   }
   return DT_OK;
 }
@@ -1067,9 +1130,9 @@ extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, 
       k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(a, rows, d->A, d->X);
       DT_LAUNCH_CHECK("k_prep_sample");
       if ((rc = unet_body(ctx, d, nb, d->film_time + (size_t)k * d->F, st))) return rc;
-      k_final_euler<<<ew_grid(rows * 32, ctx), 256, 0, st>>>(d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k],
-                                                             a, nullptr, (k == K - 1) ? d_norm : nullptr);
-      DT_LAUNCH_CHECK("k_final_euler");
+      if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k], a, nullptr,
+                                   (k == K - 1) ? d_norm : nullptr, st)))
+        return rc;
     }
   }
   return DT_OK;

@@ -2,7 +2,7 @@
 // 2-D lidar ray-marching.  All coordinate arithmetic is float64 with explicit round-to-nearest
 // intrinsics (no FMA contraction) so the flags and cell indices are bit-identical to the
 // reference's NumPy float64 code when both are fed the same float32 values.
-#include "common.cuh"
+#include "carfast.cuh"
 
 #define GEOM_THREADS 256
 
@@ -10,16 +10,17 @@
 // is_colliding_car  (common/map_utils.py:103-115)
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEOM_THREADS)
-k_collide_car(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+k_collide_car(MapView m, QMapView q, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
               int64_t stride, int64_t B, uint8_t* __restrict__ out, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
-  uint16_t* s_nbr = reinterpret_cast<uint16_t*>(s_map + m.bytes);
-  dt_stage_map(s_map, &bar, m);
-  dt_build_nbr(s_map, s_nbr, m.rows, m.cols);
-  __syncthreads();
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_map + m.bytes);
+  dt_stage_maps(s_map, s_q, &bar, m, q);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = dt_car_test_nbr(s_map, s_nbr, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
+    const float xs = x[i * stride], ys = y[i * stride], ths = th[i * stride];
+    float sn, cs;
+    dt_sincos_fast(ths, sn, cs);
+    const int r = dt_car_fast(s_map, dt_qmap_addr(s_q, q), q, m.rows, m.cols, xs, ys, ths, sn, cs);
     if (r & 4) atomicMin(status, DT_E_INDEX);
     out[i] = (uint8_t)(r & 1);
   }
@@ -324,8 +325,13 @@ extern "C" int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const
   if (B <= 0) return DT_OK;
   if (!x || !y || !theta || !flags_out) return dt_fail(ctx, DT_E_ARG, "dt_collide_car: null pointer");
   MapView m = dt_map_view(ctx);
-  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, 3 * m.bytes, (cudaStream_t)stream>>>(
-      m, x, y, theta, stride, B, flags_out, ctx->d_status);
+  QMapView q = dt_qmap_view(ctx);
+  if (m.bytes + q.bytes > 48 * 1024) {  // beyond the default dynamic shared memory limit: exact code only
+    q.g = nullptr;
+    q.bytes = 0;
+  }
+  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
+      m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
   DT_LAUNCH_CHECK("k_collide_car");
   return DT_OK;
 }

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libditree.so")
+# DITREE_LIB selects another build of the same library (kernel A/B tuning); there is still no fallback
+LIB_PATH = os.environ.get("DITREE_LIB") or os.path.join(HERE, "libditree.so")
 
 c_i64 = C.c_int64
 c_p = C.c_void_p

@@ -8,7 +8,10 @@
 // size 1) let (k, j) be the nearest grid vertex and (su, sw) in [-0.5, 0.5] the signed offsets from it:
 // |sw|, |su| are the distances to the nearest vertical / horizontal cell edge, su^2 + sw^2 the squared
 // distance to the nearest corner, and the signs select one of the four cells around the vertex.  A table
-// built by dt_set_map (ctx.cu) holds, per vertex, a 4-bit neighbourhood code for each of those quadrants.
+// built by dt_set_map (ctx.cu) holds, per vertex and quadrant, one 32-bit word with the neighbourhood flags at
+// the sign-bit positions of its four bytes; the signed margins of the three geometric tests are gathered
+// into one register by two byte permutes (their top bytes carry the signs) and ANDed with that word, so the
+// whole decision is branch-free and costs ~20 instructions per ball.
 // Rounding to the nearest integer is one fp32 add of 1.5 * 2^23 (the integer lands in the mantissa).
 //
 // Everything is fp32; a decision whose margin to its threshold is below the guard band `eps` is
@@ -30,7 +33,7 @@
 #define DT_SC_MAX 8192.0f
 
 struct QMapView {
-  const uint16_t* g;  // (rows + 2 DT_QPAD + 1) x (cols + 2 DT_QPAD + 1) vertex codes, padded to `bytes`;
+  const uint32_t* g;  // (rows + 2 DT_QPAD + 1) x (cols + 2 DT_QPAD + 1) vertices x 4 quadrant words (`bytes`);
                       // nullptr -> exact code only
   int bytes, pitch;
   int bias;           // -(bits of 1.5 * 2^23) * (pitch + 1): turns the two magic-add bit patterns into an index
@@ -55,8 +58,8 @@ static inline QMapView dt_qmap_view(const dt_ctx* ctx) {
 }
 
 #ifdef __CUDACC__
-// Stage the occupancy grid and the quadrant map with two bulk TMA copies on one mbarrier.
-__device__ __forceinline__ void dt_stage_maps(uint8_t* dst_map, uint16_t* dst_q, uint64_t* bar, const MapView& m,
+// Stage the occupancy grid and the quadrant table with two bulk TMA copies on one mbarrier.
+__device__ __forceinline__ void dt_stage_maps(uint8_t* dst_map, uint32_t* dst_q, uint64_t* bar, const MapView& m,
                                               const QMapView& q) {
   const uint32_t bar_a = dt_smem_u32(bar);
   if (threadIdx.x == 0) {
@@ -97,15 +100,20 @@ static __device__ __noinline__ float2 dt_sincos_slow(float th) {
   return r;
 }
 
-// sin / cos of a heading: two-term Cody-Waite reduction to [-pi, pi] and the MUFU approximations.
-// |error| <= DT_SC_ERR for |th| <= DT_SC_MAX; larger (or non-finite) headings take libm's sincosf.
+// sin / cos of a heading with |th| <= DT_SC_MAX: two-term Cody-Waite reduction to [-pi, pi] and the MUFU
+// approximations; |error| <= DT_SC_ERR.  (Garbage, but finite or NaN, outside that range: callers check.)
+__device__ __forceinline__ void dt_sincos_mufu(float th, float& sn, float& cs) {
+  const float kf = __fadd_rn(__fmaf_rn(th, 0.15915494f, 12582912.0f), -12582912.0f);  // rint(th / 2pi)
+  float r = __fmaf_rn(kf, -6.2831855f, th);
+  r = __fmaf_rn(kf, 1.7484555e-7f, r);
+  sn = __sinf(r);
+  cs = __cosf(r);
+}
+
+// any heading: larger (or non-finite) ones take libm's sincosf
 __device__ __forceinline__ void dt_sincos_fast(float th, float& sn, float& cs) {
   if (fabsf(th) <= DT_SC_MAX) {
-    const float kf = __fadd_rn(__fmaf_rn(th, 0.15915494f, 12582912.0f), -12582912.0f);  // rint(th / 2pi)
-    float r = __fmaf_rn(kf, -6.2831855f, th);
-    r = __fmaf_rn(kf, 1.7484555e-7f, r);
-    sn = __sinf(r);
-    cs = __cosf(r);
+    dt_sincos_mufu(th, sn, cs);
   } else {
     const float2 r = dt_sincos_slow(th);
     sn = r.x;
@@ -113,50 +121,73 @@ __device__ __forceinline__ void dt_sincos_fast(float th, float& sn, float& cs) {
   }
 }
 
-// One ball at grid coordinates (w, u), both inside [0.4, pitch - 1.4].  Sets bit 0 of `res` when it collides
-// and bit 1 when a decision is inside the guard band.  Branch-free.
-__device__ __forceinline__ unsigned dt_ball_fast(uint32_t q_addr, const QMapView& q, float w, float u) {
+__device__ __forceinline__ uint32_t dt_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// One ball at grid coordinates (w, u), both inside [0.4, pitch - 1.4].
+//   hit : some flag bit set <=> the ball collides          (bits 7, 15, 23, 31)
+//   amb : some flag bit set <=> a wall-dependent decision is inside the guard band   (bits 7, 15, 23)
+//   cell: distance to the nearest cell border (a floor decision; ambiguous when < eps)
+__device__ __forceinline__ void dt_ball_fast(uint32_t q_addr, const QMapView& q, float w, float u, uint32_t& hit,
+                                             uint32_t& amb, float& cell) {
   const float MR = 12582912.0f;  // 1.5 * 2^23: adding it (round to nearest) leaves rint(v) in the mantissa
   const float tu = __fadd_rn(u, MR), tw = __fadd_rn(w, MR);
   const float su = __fsub_rn(u, __fsub_rn(tu, MR)), sw = __fsub_rn(w, __fsub_rn(tw, MR));  // exact, in [-0.5, 0.5]
-  const uint32_t addr = q_addr + 2u * (uint32_t)(__float_as_int(tu) * q.pitch + __float_as_int(tw));
-  uint32_t code;
-  asm("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(addr));
-  // quadrant: sign of su -> bit 3, sign of sw -> bit 2 of the shift (bits 30 of both are 0: |s| < 2)
-  const unsigned nib = code >> (((__float_as_uint(su) >> 28) | (__float_as_uint(sw) >> 29)) & 12u);
+  // vertex (tu, tw) -> 16-byte entry; quadrant word: sign of su -> +8, sign of sw -> +4 (bits 30 are 0: |s| < 2)
+  const uint32_t quad = ((__float_as_uint(su) >> 28) | (__float_as_uint(sw) >> 29)) & 12u;
+  const uint32_t addr = q_addr + 16u * (uint32_t)(__float_as_int(tu) * q.pitch + __float_as_int(tw)) + quad;
+  uint32_t word;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
   const float r = 0.1f;
   const float fx = fabsf(sw), fy = fabsf(su);
-  const float tx = fx - r, ty = fy - r;
-  const float td = __fmaf_rn(sw, sw, su * su) - r * r;
-  const bool b0 = (nib & 1u) != 0, b1 = (nib & 2u) != 0, b2 = (nib & 4u) != 0, b3 = (nib & 8u) != 0;
-  const bool hit = b3 | (b0 & (tx < 0.0f)) | (b1 & (ty < 0.0f)) | (b2 & (td < 0.0f));
-  // guard band: cell borders (fx, fy ~ 0), side thresholds (only where that side is a wall), corner disc
-  const bool amb = (fminf(fx, fy) < q.eps) | (b0 & (fabsf(tx) < q.eps)) | (b1 & (fabsf(ty) < q.eps)) |
-                   (b2 & (fabsf(td) < 0.4f * q.eps));
-  return (hit ? 1u : 0u) | (amb ? 2u : 0u);
+  const float tx = fx - r, ty = fy - r;                         // < 0: reaches past that cell edge
+  const float td = __fmaf_rn(sw, sw, su * su) - r * r;          // < 0: inside the corner disc
+  // top bytes (sign + exponent) of the margins, one per byte lane: the table word keeps only the signs
+  const uint32_t sg = dt_prmt(dt_prmt(__float_as_uint(tx), __float_as_uint(ty), 0x7373u), __float_as_uint(td), 0x7710u);
+  hit = (sg | 0x80000000u) & word;
+  const float ax = fabsf(tx) - q.eps, ay = fabsf(ty) - q.eps, ad = fabsf(td) - 0.4f * q.eps;  // < 0: ambiguous
+  const uint32_t ag = dt_prmt(dt_prmt(__float_as_uint(ax), __float_as_uint(ay), 0x7373u), __float_as_uint(ad), 0x7710u);
+  amb = ag & word & 0x00808080u;
+  cell = fminf(fx, fy);
 }
 
 // exact decision for the rare ambiguous state (kept out of line: float64 sincos + 8 hypot)
 static __device__ __noinline__ int dt_car_test_exact(const uint8_t* __restrict__ grid, int R, int C, float x, float y,
-                                              float th) {
+                                                     float th) {
   return dt_car_test(grid, R, C, x, y, th);
 }
 
-// is_colliding_car given the heading's sine / cosine from dt_sincos_fast.  `q_addr` = dt_qmap_addr(...).
-// Returns 0/1, or 1|4 when the reference would raise IndexError (only on maps without a quadrant table).
-__device__ __forceinline__ uint32_t dt_qmap_addr(const uint16_t* s_q, const QMapView& q) {
-  return dt_smem_u32(s_q) + 2u * (uint32_t)q.bias;
+__device__ __forceinline__ uint32_t dt_qmap_addr(const uint32_t* s_q, const QMapView& q) {
+  return dt_smem_u32(s_q) + 16u * (uint32_t)q.bias;
 }
 
-__device__ __forceinline__ int dt_car_fast(const uint8_t* __restrict__ grid, uint32_t q_addr, const QMapView& q, int R,
-                                           int C, float x, float y, float th, float sn, float cs) {
-  if (!q.g) return dt_car_test_exact(grid, R, C, x, y, th);
+// Fast part of is_colliding_car given the heading's sine / cosine: returns the collision flag and sets
+// `ambiguous` when the exact code (dt_car_test_exact) must decide instead.  Needs the quadrant table.
+__device__ __forceinline__ bool dt_car_fast(uint32_t q_addr, const QMapView& q, float x, float y, float sn, float cs,
+                                            bool& ambiguous) {
   // car centre in padded grid coordinates, clamped into the padding (NaN -> 0.5: a padding cell, collides)
   const float wc = fminf(fmaxf(__fadd_rn(x, q.cxp), 0.5f), q.wmax);
   const float uc = fminf(fmaxf(__fsub_rn(q.cyp, y), 0.5f), q.umax);
-  const unsigned a = dt_ball_fast(q_addr, q, __fmaf_rn(cs, 0.075f, wc), __fmaf_rn(sn, -0.075f, uc));
-  const unsigned b = dt_ball_fast(q_addr, q, __fmaf_rn(cs, -0.075f, wc), __fmaf_rn(sn, 0.075f, uc));
-  if ((a | b) & 2u) return dt_car_test_exact(grid, R, C, x, y, th);
-  return (int)((a | b) & 1u);
+  uint32_t ha, hb, aa, ab;
+  float ca, cb;
+  dt_ball_fast(q_addr, q, __fmaf_rn(cs, 0.075f, wc), __fmaf_rn(sn, -0.075f, uc), ha, aa, ca);
+  dt_ball_fast(q_addr, q, __fmaf_rn(cs, -0.075f, wc), __fmaf_rn(sn, 0.075f, uc), hb, ab, cb);
+  ambiguous = ((aa | ab) != 0u) | (fminf(ca, cb) < q.eps);
+  return (ha | hb) != 0u;
+}
+
+// is_colliding_car for one state (any heading); returns 0/1, or 1|4 when the reference would raise IndexError
+__device__ __forceinline__ int dt_car_any(const uint8_t* __restrict__ grid, uint32_t q_addr, const QMapView& q, int R,
+                                          int C, float x, float y, float th) {
+  if (!q.g || !(fabsf(th) <= DT_SC_MAX)) return dt_car_test_exact(grid, R, C, x, y, th);
+  float sn, cs;
+  dt_sincos_mufu(th, sn, cs);
+  bool amb;
+  const bool hit = dt_car_fast(q_addr, q, x, y, sn, cs, amb);
+  if (amb) return dt_car_test_exact(grid, R, C, x, y, th);
+  return hit ? 1 : 0;
 }
 #endif  // __CUDACC__

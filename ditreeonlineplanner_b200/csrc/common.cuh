@@ -12,6 +12,7 @@
 
 #define DT_MAX_MAP_CELLS 16384  // 128 x 128; the reference's grids are <= 31 x 31
 #define DT_QPAD 2               // padding rings of the collision fast path's quadrant table (carfast.cuh)
+#define DT_QMAP_MAX_BYTES (96u * 1024u)  // larger tables (maps beyond ~72 x 72) use the exact code only
 
 struct dt_denoiser;  // denoiser.cu
 
@@ -23,9 +24,10 @@ struct dt_ctx {
   int rows = 0, cols = 0;
   double s_global = 1.0;
   int map_bytes = 0;  // padded size
-  // quadrant map of the car collision fast path (carfast.cuh), (rows+5) x (cols+5) uint16, padded to 16 B;
+  // quadrant map of the car collision fast path (carfast.cuh), (rows+5) x (cols+5) x 4 uint32;
   // absent (qmap_bytes == 0) on tall maps where the reference's diagonal lookup can raise IndexError
-  uint16_t* d_qmap = nullptr;
+  // and on maps too large for shared memory
+  uint32_t* d_qmap = nullptr;
   int qmap_bytes = 0;
   size_t map_capacity = 0, qmap_capacity = 0;
   bool prop_attr_set = false;  // dynamic shared memory opt-in of the propagate kernels done on this device

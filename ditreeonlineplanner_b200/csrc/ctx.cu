@@ -124,44 +124,41 @@ extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int col
   for (int i = 0; i < rows * cols; ++i) bytes[i] = (grid_host[i] == 1.0f) ? 1 : (grid_host[i] != 0.0f ? 2 : 0);
   // Quadrant table of the car collision fast path (carfast.cuh).  The grid is padded by DT_QPAD rings of
   // "always collides" cells (a ball centre outside the grid collides, common/map_utils.py:255-259) and the
-  // table is indexed by the grid VERTEX (k, j) nearest to the ball centre; each entry holds four nibbles, one
-  // per cell quadrant touching that vertex: nibble (a, b) at bit 8a + 4b describes the cell above (a = 1) /
-  // below (a = 0) and left (b = 1) / right (b = 0) of the vertex, i.e. the ball sits in the lower (a = 1) /
-  // upper half and right (b = 1) / left half of that cell:
-  //   bit 0  the side neighbour in x on that half is a wall   (index clipped as map_utils.py:281-296)
-  //   bit 1  the side neighbour in y on that half is a wall
-  //   bit 2  the diagonal neighbour of that quadrant is a wall (row clipped with R-1, column with R-1: sic, :326)
-  //   bit 3  collides wherever the ball is: padding cell, own cell is a wall, or any of the four diagonal
-  //          cells lies outside the grid (`invalid_cell`, :322-327, which makes every border cell collide)
-  // Built only when rows <= cols: on taller maps the row-count clip can index past the last column (NumPy
-  // raises IndexError) and the exact code, which reports that, is used instead.
-  std::vector<uint16_t> q;
+  // table is indexed by the grid VERTEX (k, j) nearest to the ball centre; each vertex holds four 32-bit
+  // words, one per cell quadrant touching it: word 2a + b describes the cell above (a = 1) / below (a = 0)
+  // and left (b = 1) / right (b = 0) of the vertex, i.e. the ball sits in the lower (a = 1) / upper half and
+  // right (b = 1) / left half of that cell.  The flags sit at the sign-bit position of one byte each, so
+  // the kernel can AND them with the gathered top bytes of its signed margins:
+  //   bit  7  the side neighbour in x on that half is a wall   (index clipped as map_utils.py:281-296)
+  //   bit 15  the side neighbour in y on that half is a wall
+  //   bit 23  the diagonal neighbour of that quadrant is a wall (row clipped with R-1, column with R-1: sic, :326)
+  //   bit 31  collides wherever the ball is: padding cell, own cell is a wall, or any of the four diagonal
+  //           cells lies outside the grid (`invalid_cell`, :322-327, which makes every border cell collide)
+  // Built only when rows <= cols (on taller maps the row-count clip can index past the last column: NumPy
+  // raises IndexError, and the exact code, which reports that, is used instead) and when it fits in
+  // DT_QMAP_MAX_BYTES of shared memory.
+  std::vector<uint32_t> q;
   int qpadded = 0;
-  if (rows <= cols) {
-    const int VR = rows + 2 * DT_QPAD + 1, VC = cols + 2 * DT_QPAD + 1;
-    qpadded = ((VR * VC * 2 + 15) / 16) * 16;
-    q.assign(qpadded / 2, 0x8888);
+  const int VR = rows + 2 * DT_QPAD + 1, VC = cols + 2 * DT_QPAD + 1;
+  if (rows <= cols && (size_t)VR * VC * 16 <= DT_QMAP_MAX_BYTES) {
+    qpadded = VR * VC * 16;
+    q.assign((size_t)VR * VC * 4, 0x80000000u);
     auto wall = [&](int r, int c) { return bytes[r * cols + c] == 1; };
     auto clip = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
     for (int k = 0; k < VR; ++k)
-      for (int j = 0; j < VC; ++j) {
-        unsigned e = 0;
+      for (int j = 0; j < VC; ++j)
         for (int a = 0; a < 2; ++a)
           for (int b = 0; b < 2; ++b) {
             const int r = k - a - DT_QPAD, c = j - b - DT_QPAD;  // the cell of this quadrant, grid indices
-            unsigned nib = 8u;
-            if (r >= 0 && r < rows && c >= 0 && c < cols) {
-              const bool border = (r == 0) | (r == rows - 1) | (c == 0) | (c == cols - 1);  // a diagonal is outside
-              nib = (wall(r, c) || border) ? 8u : 0u;
-              const int sx = b ? 1 : -1, sy = a ? 1 : -1;
-              nib |= wall(r, clip(c + sx, 0, cols - 1)) ? 1u : 0u;
-              nib |= wall(clip(r + sy, 0, rows - 1), c) ? 2u : 0u;
-              nib |= wall(clip(r + sy, 0, rows - 1), clip(c + sx, 0, rows - 1)) ? 4u : 0u;  // sic: rows - 1
-            }
-            e |= nib << (8 * a + 4 * b);
+            if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+            const bool border = (r == 0) | (r == rows - 1) | (c == 0) | (c == cols - 1);  // a diagonal is outside
+            uint32_t w = (wall(r, c) || border) ? 0x80000000u : 0u;
+            const int sx = b ? 1 : -1, sy = a ? 1 : -1;
+            w |= wall(r, clip(c + sx, 0, cols - 1)) ? 0x80u : 0u;
+            w |= wall(clip(r + sy, 0, rows - 1), c) ? 0x8000u : 0u;
+            w |= wall(clip(r + sy, 0, rows - 1), clip(c + sx, 0, rows - 1)) ? 0x800000u : 0u;  // sic: rows - 1
+            q[((size_t)k * VC + j) * 4 + 2 * a + b] = w;
           }
-        q[k * VC + j] = (uint16_t)e;
-      }
   }
   cudaStream_t st = (cudaStream_t)stream;
   if ((size_t)padded > ctx->map_capacity || (size_t)qpadded > ctx->qmap_capacity) {

@@ -14,13 +14,11 @@ k_collide_car(MapView m, QMapView q, const float* __restrict__ x, const float* _
               int64_t stride, int64_t B, uint8_t* __restrict__ out, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
-  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_map + m.bytes);
+  uint32_t* s_q = reinterpret_cast<uint32_t*>(s_map + m.bytes);
   dt_stage_maps(s_map, s_q, &bar, m, q);
+  const uint32_t q_addr = dt_qmap_addr(s_q, q);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    const float xs = x[i * stride], ys = y[i * stride], ths = th[i * stride];
-    float sn, cs;
-    dt_sincos_fast(ths, sn, cs);
-    const int r = dt_car_fast(s_map, dt_qmap_addr(s_q, q), q, m.rows, m.cols, xs, ys, ths, sn, cs);
+    const int r = dt_car_any(s_map, q_addr, q, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
     if (r & 4) atomicMin(status, DT_E_INDEX);
     out[i] = (uint8_t)(r & 1);
   }

@@ -9,15 +9,25 @@
 // the float64 reference decides them on the fp32 state (guard-banded fp32 fast paths that defer to the
 // float64 code near a threshold), so flags are bit-exact vs NumPy given the same states.
 //
-// Two kernels share the step function, so every layout yields the same bits:
-//   k_propagate<false>  generic element strides (coalesced for struct-of-arrays buffers)
-//   k_propagate<true>   the reference's row layouts -- actions (B, T, 2), trajectory (B, S, 6) -- staged
-//                       through warp-private shared memory in chunks of PROP_CH steps, so global memory
-//                       sees whole 32-byte sectors (per-thread row accesses would touch 8 / 24 bytes of
-//                       each 512 / 1200-byte row per step)
+// Two kernels share the step function, so every layout yields the same bits (template flag: the collision
+// fast path's table exists for this map):
+//   k_propagate_strided  generic element strides (coalesced for struct-of-arrays buffers)
+//   k_propagate_rows     the reference's row layouts -- state (B, 6), actions (B, T, 2), trajectory (B, S, 6)
+//                        -- staged through warp-private shared memory in chunks of PROP_CH steps, so global
+//                        memory sees whole 32-byte sectors (per-thread row accesses would touch 8 / 24
+//                        bytes of each 512 / 1200-byte row per step)
 #include "carfast.cuh"
 
 #define PROP_THREADS 128
+#ifndef PROP_PF
+#define PROP_PF 1     // action prefetch distance of the strided kernel, steps (register ring)
+#endif
+// trajectory stores: never re-read by this kernel -> streaming (evict-first) stores
+#ifdef PROP_PLAIN_ST
+#define PROP_ST(p, v) (*(p) = (v))
+#else
+#define PROP_ST(p, v) __stcs((p), (v))
+#endif
 #define PROP_WARPS (PROP_THREADS / 32)
 
 struct PropArgs {
@@ -52,7 +62,7 @@ __device__ __forceinline__ float ex2_approx(float v) {
   return r;
 }
 
-// CarEnv._update_state (car_env.py:356-396), explicit Euler with dt = 0.02
+// CarEnv._update_state (car_env.py:356-396), explicit Euler with dt = 0.02; leaves sn / cs stale
 __device__ __forceinline__ void car_step(Car& c, float u0, float u1) {
   // clip to the action space (car_env.py:371; bounds car_env.py:594-597)
   u0 = fminf(fmaxf(u0, -10.0f), 10.0f);
@@ -73,19 +83,6 @@ __device__ __forceinline__ void car_step(Car& c, float u0, float u1) {
   c.v += dt * dv;
   c.D += dt * u0;
   c.dl += dt * u1;
-  dt_sincos_fast(c.psi, c.sn, c.cs);
-}
-
-// ||p - goal|| < 0.5 (car_env.py:341-350) decided exactly as the float64 reference does: fp32 squared
-// distance when it is clear of 0.25 by more than its rounding error, else the float64 expression (and
-// on the knife edge the square root itself).
-__device__ __forceinline__ bool goal_test(float x, float y, float gxf, float gyf) {
-  const float fx = x - gxf, fy = y - gyf;
-  const float f2 = fx * fx + fy * fy;
-  if (fabsf(f2 - 0.25f) > 1.0e-4f * fmaxf(1.0f, f2)) return f2 < 0.25f;
-  const double ex = xsub((double)x, (double)gxf), ey = xsub((double)y, (double)gyf);
-  const double d2 = xadd(xmul(ex, ex), xmul(ey, ey));
-  return (fabs(d2 - 0.25) < 1.0e-9) ? (__dsqrt_rn(d2) < 0.5) : (d2 < 0.25);
 }
 
 struct EdgeState {
@@ -93,182 +90,303 @@ struct EdgeState {
   bool alive;
 };
 
-// one step of BasePlanner.propagate_action_sequence_env (planners/base_planner.py:281-317) for a live edge
-__device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0, float u1, bool stop,
-                                          const uint8_t* s_map, uint32_t s_q, const MapView& m,
-                                          const QMapView& q, float gx, float gy, int* status) {
-  car_step(c, u0, u1);
-  // goal test (car_env.py:341-350) and collision (planners/base_planner.py:306) on the new state
-  const bool in_goal = goal_test(c.x, c.y, gx, gy);
-  const int hit = dt_car_fast(s_map, s_q, q, m.rows, m.cols, c.x, c.y, c.psi, c.sn, c.cs);
-  if (hit & 4) atomicMin(status, DT_E_INDEX);
-  const bool coll = (hit & 1) != 0;
-  if (coll && e.first < 0) e.first = i;
-  if (coll && stop) {
-    e.alive = false;  // collision ends the edge, the goal flag is ignored (base_planner.py:306-312)
-  } else if (in_goal) {
-    e.done = i;       // goal reached: remaining actions are zeroed, loop breaks (:314-317)
-    e.alive = false;
-  }
+// Rare path of a step, out of line: the heading left the MUFU range, a collision decision fell inside the
+// guard band, or the goal distance is within rounding of 0.5.  Re-decides everything exactly:
+//   collision  : float64 code (dt_car_test, common.cuh)
+//   goal       : ||p - goal|| < 0.5 as the float64 reference computes it (car_env.py:341-350); squares
+//                compared, the square root taken only on the knife edge
+// Returns (sn, cs, flags): sin / cos of the heading (recomputed by libm when it left the MUFU range) and
+// flag bits 0 collides, 1 in goal, 2 the reference would raise IndexError.
+static __device__ __noinline__ float4 edge_slow(const uint8_t* __restrict__ grid, int R, int C, float x, float y,
+                                                float th, float gxf, float gyf, float sn, float cs) {
+  if (!(fabsf(th) <= DT_SC_MAX)) sincosf(th, &sn, &cs);
+  const int hit = dt_car_test(grid, R, C, x, y, th);
+  const double ex = xsub((double)x, (double)gxf), ey = xsub((double)y, (double)gyf);
+  const double d2 = xadd(xmul(ex, ex), xmul(ey, ey));
+  const bool in_goal = (fabs(d2 - 0.25) < 1.0e-9) ? (__dsqrt_rn(d2) < 0.5) : (d2 < 0.25);
+  return make_float4(sn, cs, __int_as_float((hit & 1) | (in_goal ? 2 : 0) | (hit & 4)), 0.f);
 }
 
-#define PROP_CH 4                        // steps per staged chunk
-#define PROP_APITCH (PROP_CH * 2 + 4)    // 12 words: float4 rows, conflict-free for per-lane 16-byte accesses
-#define PROP_TPITCH (PROP_CH * 6 + 4)    // 28 words
-#define PROP_STAGE_WORDS (32 * (PROP_APITCH + PROP_TPITCH))
+// one step of BasePlanner.propagate_action_sequence_env (planners/base_planner.py:281-317) for a live edge
+template <bool kTable>
+__device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0, float u1, bool stop,
+                                          const uint8_t* s_map, uint32_t s_q, const MapView& m, const QMapView& q,
+                                          float gx, float gy, int* status) {
+  car_step(c, u0, u1);
+  dt_sincos_mufu(c.psi, c.sn, c.cs);
+  // goal test (car_env.py:341-350): fp32 squared distance, trusted when clear of 0.25 by more than its error
+  const float fx = c.x - gx, fy = c.y - gy;
+  const float f2 = fx * fx + fy * fy;
+  bool in_goal = f2 < 0.25f;
+  bool rare = !(fabsf(f2 - 0.25f) > 1.0e-4f * fmaxf(1.0f, f2)) | !(fabsf(c.psi) <= DT_SC_MAX);
+  // collision (planners/base_planner.py:306) on the new state
+  bool coll = false;
+  if (kTable) {
+    bool amb;
+    coll = dt_car_fast(s_q, q, c.x, c.y, c.sn, c.cs, amb);
+    rare |= amb;
+  } else {
+    rare = true;
+  }
+  if (rare) {
+    const float4 sl = edge_slow(s_map, m.rows, m.cols, c.x, c.y, c.psi, gx, gy, c.sn, c.cs);
+    c.sn = sl.x;
+    c.cs = sl.y;
+    const int r = __float_as_int(sl.z);
+    coll = (r & 1) != 0;
+    in_goal = (r & 2) != 0;
+    if (r & 4) atomicMin(status, DT_E_INDEX);
+  }
+  // collision ends the edge and the goal flag is then ignored (base_planner.py:306-312); goal reached: the
+  // remaining actions are zeroed and the loop breaks (:314-317)
+  e.first = (coll & (e.first < 0)) ? i : e.first;
+  const bool die_c = coll & stop;
+  const bool die_g = in_goal & !die_c;
+  e.done = die_g ? i : e.done;
+  e.alive = !(die_c | die_g);
+}
 
-template <bool kRows>
-__global__ void __launch_bounds__(PROP_THREADS)
-k_propagate(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
+// ---------------------------------------------------------------------------------------------
+// Generic element strides (coalesced for struct-of-arrays buffers); next step's action prefetched
+// ---------------------------------------------------------------------------------------------
+template <bool kTable>
+__global__ void __launch_bounds__(PROP_THREADS, 6)
+k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint64_t bar;
   uint8_t* s_map = s_dyn;
-  uint16_t* s_qp = reinterpret_cast<uint16_t*>(s_dyn + m.bytes);
+  uint32_t* s_qp = reinterpret_cast<uint32_t*>(s_dyn + m.bytes);
+  dt_stage_maps(s_map, s_qp, &bar, m, q);
+  const uint32_t s_q = dt_qmap_addr(s_qp, q);
+  const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
+  for (int64_t b = blockIdx.x * (int64_t)PROP_THREADS + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * PROP_THREADS) {
+    const float* s0 = a.state0 + b * a.s_cand;
+    Car c;
+    c.x = s0[0]; c.y = s0[a.s_comp]; c.psi = s0[2 * a.s_comp]; c.v = s0[3 * a.s_comp]; c.D = s0[4 * a.s_comp];
+    c.dl = s0[5 * a.s_comp];
+    dt_sincos_fast(c.psi, c.sn, c.cs);
+    const float* act = a.actions + b * a.a_cand;
+    float* tr = a.traj ? a.traj + b * a.t_cand : nullptr;
+    EdgeState e = {-1, -1, true};
+    // actions are fetched PROP_PF steps ahead (register ring): under the trajectory's write traffic a
+    // global load takes ~1 us, several steps of compute
+    float n0[PROP_PF], n1[PROP_PF];
+#pragma unroll
+    for (int k = 0; k < PROP_PF; ++k) {
+      n0[k] = 0.f; n1[k] = 0.f;
+      if (k < a.S) { n0[k] = __ldg(act + k * a.a_step); n1[k] = __ldg(act + k * a.a_step + a.a_comp); }
+    }
+    for (int i0 = 0; i0 < a.S; i0 += PROP_PF) {
+#pragma unroll
+    for (int k = 0; k < PROP_PF; ++k) {
+      const int i = i0 + k;
+      if (i >= a.S) break;
+      const float u0 = n0[k], u1 = n1[k];
+      if (i + PROP_PF < a.S) {
+        n0[k] = __ldg(act + (i + PROP_PF) * a.a_step);
+        n1[k] = __ldg(act + (i + PROP_PF) * a.a_step + a.a_comp);
+      }
+      // one store per component for the whole warp (live lanes: the new state, finished lanes: zeros), so
+      // a 128-byte line of a struct-of-arrays trajectory is written once, never as two partial writes
+      const bool was_alive = e.alive;
+      if (was_alive) edge_step<kTable>(c, e, i, u0, u1, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
+      if (tr) {
+        float* o = tr + i * a.t_step;
+        PROP_ST(o, was_alive ? c.x : 0.f);
+        PROP_ST(o + a.t_comp, was_alive ? c.y : 0.f);
+        PROP_ST(o + 2 * a.t_comp, was_alive ? c.psi : 0.f);
+        PROP_ST(o + 3 * a.t_comp, was_alive ? c.v : 0.f);
+        PROP_ST(o + 4 * a.t_comp, was_alive ? c.D : 0.f);
+        PROP_ST(o + 5 * a.t_comp, was_alive ? c.dl : 0.f);
+      }
+    }
+    }
+    if (a.state_out) {
+      float* so = a.state_out + b * a.s_cand;
+      so[0] = c.x; so[a.s_comp] = c.y; so[2 * a.s_comp] = c.psi; so[3 * a.s_comp] = c.v; so[4 * a.s_comp] = c.D;
+      so[5 * a.s_comp] = c.dl;
+    }
+    if (a.first_coll) a.first_coll[b] = e.first;
+    if (a.done_step) a.done_step[b] = e.done;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row layouts: state (B, 6), actions (B, T, 2), trajectory (B, S, 6), all rows 16-byte aligned.
+// Each warp owns tasks of 32 consecutive candidates and walks them in chunks of PROP_CH steps.  A chunk's
+// actions (32 B per candidate) arrive in a double-buffered warp-private staging area by cp.async, issued
+// one chunk ahead -- across task boundaries, together with the next task's start states -- so no global
+// load latency is exposed; a chunk's trajectory (96 B per candidate) is written to staging rows by the
+// owning lanes and copied out by the whole warp as 64-byte / 32-byte row segments.
+// Staging rows are padded to 12 / 28 words: per-lane 16-byte accesses (row stride 3 resp. 7 bank groups
+// modulo 8) and the copy mapping (a quarter-warp = 8 different candidates) are both conflict-free.
+// ---------------------------------------------------------------------------------------------
+#define PROP_CH 4                        // steps per chunk
+#define PROP_APITCH (PROP_CH * 2 + 4)    // words
+#define PROP_TPITCH (PROP_CH * 6 + 4)
+#define PROP_SPITCH 6                    // start states: 24-byte rows, as in global memory
+#define PROP_WARP_WORDS (32 * (2 * PROP_APITCH + PROP_TPITCH + PROP_SPITCH))
+// 4 warps x 4 blocks per SM at <= 128 registers: no spills (a spilled value costs a local load that misses the
+// store-churned L1); more, smaller-register warps measured slower (tools/build_variant.sh)
+#ifndef PROP_RTHREADS
+#define PROP_RTHREADS 128
+#endif
+#ifndef PROP_RMINB
+#define PROP_RMINB 4
+#endif
+#define PROP_RWARPS (PROP_RTHREADS / 32)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool kTable>
+__global__ void __launch_bounds__(PROP_RTHREADS, PROP_RMINB)
+k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint64_t bar;
+  uint8_t* s_map = s_dyn;
+  uint32_t* s_qp = reinterpret_cast<uint32_t*>(s_dyn + m.bytes);
   dt_stage_maps(s_map, s_qp, &bar, m, q);
   const uint32_t s_q = dt_qmap_addr(s_qp, q);
   const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  if (!kRows) {
-    for (int64_t b = blockIdx.x * (int64_t)PROP_THREADS + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * PROP_THREADS) {
-      const float* s0 = a.state0 + b * a.s_cand;
-      Car c;
-      c.x = s0[0]; c.y = s0[a.s_comp]; c.psi = s0[2 * a.s_comp]; c.v = s0[3 * a.s_comp]; c.D = s0[4 * a.s_comp];
-      c.dl = s0[5 * a.s_comp];
-      dt_sincos_fast(c.psi, c.sn, c.cs);
-      const float* act = a.actions + b * a.a_cand;
-      float* tr = a.traj ? a.traj + b * a.t_cand : nullptr;
-      EdgeState e = {-1, -1, true};
-      for (int i = 0; i < a.S; ++i) {
-        if (e.alive) {
-          const float u0 = __ldg(act + i * a.a_step), u1 = __ldg(act + i * a.a_step + a.a_comp);
-          edge_step(c, e, i, u0, u1, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
-          if (tr) {
-            float* o = tr + i * a.t_step;
-            o[0] = c.x; o[a.t_comp] = c.y; o[2 * a.t_comp] = c.psi; o[3 * a.t_comp] = c.v; o[4 * a.t_comp] = c.D;
-            o[5 * a.t_comp] = c.dl;
-          }
-        } else if (tr) {
-          float* o = tr + i * a.t_step;
-          o[0] = 0.f; o[a.t_comp] = 0.f; o[2 * a.t_comp] = 0.f; o[3 * a.t_comp] = 0.f; o[4 * a.t_comp] = 0.f;
-          o[5 * a.t_comp] = 0.f;
-        }
-      }
-      if (a.state_out) {
-        float* so = a.state_out + b * a.s_cand;
-        so[0] = c.x; so[a.s_comp] = c.y; so[2 * a.s_comp] = c.psi; so[3 * a.s_comp] = c.v; so[4 * a.s_comp] = c.D;
-        so[5 * a.s_comp] = c.dl;
-      }
-      if (a.first_coll) a.first_coll[b] = e.first;
-      if (a.done_step) a.done_step[b] = e.done;
-    }
-    return;
-  }
-
-  // ---- row layouts: each warp owns 32 consecutive candidates and a private staging area ----
-  float* s_act = reinterpret_cast<float*>(s_dyn + m.bytes + q.bytes) + (size_t)warp * PROP_STAGE_WORDS;
-  float* s_trj = s_act + 32 * PROP_APITCH;
-  // copy mapping: lane -> (candidate c8 within a group of 8, 16-byte column q4); a quarter-warp touches 8
-  // different candidates, whose rows are 3 (resp. 7) 16-byte bank groups apart modulo 8: conflict-free
+  float* s_warp = reinterpret_cast<float*>(s_dyn + m.bytes + q.bytes) + (size_t)warp * PROP_WARP_WORDS;
+  float* s_act = s_warp;                          // 2 buffers of 32 x PROP_APITCH
+  float* s_trj = s_act + 2 * 32 * PROP_APITCH;    // 32 x PROP_TPITCH
+  float* s_st = s_trj + 32 * PROP_TPITCH;         // 32 x 6
+  const uint32_t s_act_u = dt_smem_u32(s_act), s_st_u = dt_smem_u32(s_st);
+  // copy mapping: lane -> candidate c8 (+8, +16, +24) and 16-byte column q4
   const int c8 = lane & 7, q4 = lane >> 3;
-  const int64_t nwarps = (int64_t)gridDim.x * PROP_WARPS;
-  for (int64_t b0 = ((int64_t)blockIdx.x * PROP_WARPS + warp) * 32; b0 < a.B; b0 += nwarps * 32) {
-    const int64_t b = b0 + lane;
-    const bool live = b < a.B;
-    const int nb = (int)((a.B - b0 < 32) ? (a.B - b0) : 32);
-    Car c = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-    if (live) {
-      const float* s0 = a.state0 + b * a.s_cand;
-      c.x = s0[0]; c.y = s0[a.s_comp]; c.psi = s0[2 * a.s_comp]; c.v = s0[3 * a.s_comp]; c.D = s0[4 * a.s_comp];
-      c.dl = s0[5 * a.s_comp];
-      dt_sincos_fast(c.psi, c.sn, c.cs);
-    }
-    EdgeState e = {-1, -1, live};
-    const int full = a.S / PROP_CH;  // whole chunks
-    // prefetch of the next chunk's actions: 32 candidates x 2 float4 = 64 float4, two per lane
-    // (lane -> candidate lane & 7 (+8, +16, +24 over two loads of two column halves))
-    float4 pf[2];
-    auto prefetch = [&](int chunk) {
+  // (loop bounds are re-derived from kernel parameters -- constant bank operands -- instead of being kept
+  // in registers: a spilled loop invariant costs a local-memory load that misses the store-churned L1)
+#define PROP_TSTRIDE (gridDim.x * (PROP_RWARPS * 32u))
+  const uint32_t Bn = (uint32_t)a.B;  // the launcher sends B >= 2^31 to the strided kernel
+
+  // asynchronous copy of chunk `ch` of the task starting at candidate t0 into action buffer `buf`
+  // (plus that task's start states when ch == 0)
+  auto issue = [&](uint32_t t0, int ch, int buf) {
+    const int nb = (int)((Bn - t0 < 32u) ? (Bn - t0) : 32u);
+    const int cs = (a.S - ch * PROP_CH < PROP_CH) ? (a.S - ch * PROP_CH) : PROP_CH;
+    const uint32_t dst = s_act_u + (uint32_t)buf * (32 * PROP_APITCH * 4);
+#ifdef PROP_EXP_NOLOAD  // experiment: no action loads (staging rows stay zero)
+    if (cs >= 0) {
+    } else if (cs == PROP_CH) {
+#else
+    if (cs == PROP_CH) {
+#endif
+      // 32 candidates x 2 float4: lane -> candidates c8 + 8 * (q4 >> 1) (+16), column q4 & 1
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const int cand = c8 + 8 * (q4 >> 1) + 16 * g, col = q4 & 1;
-        pf[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cand < nb)
-          pf[g] = __ldg(reinterpret_cast<const float4*>(a.actions + (b0 + cand) * a.a_cand + (int64_t)chunk * (PROP_CH * 2)) + col);
+          cp_async16(dst + (uint32_t)(cand * PROP_APITCH + 4 * col) * 4,
+                     a.actions + (int64_t)(t0 + cand) * a.a_cand + ch * (PROP_CH * 2) + 4 * col);
       }
-    };
-    if (full > 0) prefetch(0);
-    for (int ch = 0; ch < full; ++ch) {
+    } else if (lane < nb) {  // ragged last chunk: each lane fetches its own cs steps (never past step S)
+      for (int i = 0; i < cs; ++i)
+        cp_async8(dst + (uint32_t)(lane * PROP_APITCH + 2 * i) * 4,
+                  a.actions + (int64_t)(t0 + lane) * a.a_cand + (ch * PROP_CH + i) * 2);
+    }
+    if (ch == 0 && lane < nb) {
+      const float* src = a.state0 + (int64_t)(t0 + lane) * 6;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int cand = c8 + 8 * (q4 >> 1) + 16 * g, col = q4 & 1;
-        *reinterpret_cast<float4*>(s_act + cand * PROP_APITCH + 4 * col) = pf[g];
-      }
+      for (int k = 0; k < 3; ++k) cp_async8(s_st_u + (uint32_t)(lane * PROP_SPITCH + 2 * k) * 4, src + 2 * k);
+    }
+  };
+
+  uint32_t t0 = (blockIdx.x * PROP_RWARPS + warp) * 32u;
+#ifdef PROP_EXP_NOLOAD
+  for (int k = lane; k < 2 * 32 * PROP_APITCH; k += 32) s_act[k] = 0.f;
+  __syncwarp();
+#endif
+  if (t0 < Bn && a.S > 0) issue(t0, 0, 0);
+  int buf = 0;
+  Car c = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  EdgeState e = {-1, -1, false};
+  while (t0 < Bn) {
+    const int nb = (int)((Bn - t0 < 32u) ? (Bn - t0) : 32u);
+    const bool live = lane < nb;
+    for (int ch = 0; ch * PROP_CH < a.S; ++ch) {
+      cp_async_wait_all();
       __syncwarp();
-      if (ch + 1 < full) prefetch(ch + 1);
-      const float4 a01 = *reinterpret_cast<const float4*>(s_act + lane * PROP_APITCH);
-      const float4 a23 = *reinterpret_cast<const float4*>(s_act + lane * PROP_APITCH + 4);
-      const float us[PROP_CH * 2] = {a01.x, a01.y, a01.z, a01.w, a23.x, a23.y, a23.z, a23.w};
+      if (ch == 0) {
+        if (live) {
+          const float2 p0 = *reinterpret_cast<const float2*>(s_st + lane * PROP_SPITCH);
+          const float2 p1 = *reinterpret_cast<const float2*>(s_st + lane * PROP_SPITCH + 2);
+          const float2 p2 = *reinterpret_cast<const float2*>(s_st + lane * PROP_SPITCH + 4);
+          c.x = p0.x; c.y = p0.y; c.psi = p1.x; c.v = p1.y; c.D = p2.x; c.dl = p2.y;
+          dt_sincos_fast(c.psi, c.sn, c.cs);
+        }
+        e.first = -1; e.done = -1; e.alive = live;
+        __syncwarp();  // start states consumed before the next task's may land
+      }
+      // next chunk (possibly the next task's first) into the other buffer
+      if ((ch + 1) * PROP_CH < a.S) issue(t0, ch + 1, buf ^ 1);
+      else if (t0 + PROP_TSTRIDE < Bn && t0 + PROP_TSTRIDE > t0) issue(t0 + PROP_TSTRIDE, 0, buf ^ 1);
+      const int cs = (a.S - ch * PROP_CH < PROP_CH) ? (a.S - ch * PROP_CH) : PROP_CH;
+      const float* ua = s_act + buf * (32 * PROP_APITCH) + lane * PROP_APITCH;
+      float* my = s_trj + lane * PROP_TPITCH;
       float o[PROP_CH * 6];
 #pragma unroll
       for (int i = 0; i < PROP_CH; ++i) {
-        if (e.alive) {
-          edge_step(c, e, ch * PROP_CH + i, us[2 * i], us[2 * i + 1], stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
+        if (e.alive && i < cs) {
+          const float2 u = *reinterpret_cast<const float2*>(ua + 2 * i);
+          edge_step<kTable>(c, e, ch * PROP_CH + i, u.x, u.y, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
           o[6 * i] = c.x; o[6 * i + 1] = c.y; o[6 * i + 2] = c.psi; o[6 * i + 3] = c.v; o[6 * i + 4] = c.D;
           o[6 * i + 5] = c.dl;
         } else {
           o[6 * i] = 0.f; o[6 * i + 1] = 0.f; o[6 * i + 2] = 0.f; o[6 * i + 3] = 0.f; o[6 * i + 4] = 0.f;
           o[6 * i + 5] = 0.f;
         }
+        // a float4 of the staging row is stored as soon as it is complete
+#pragma unroll
+        for (int j = (6 * i) / 4; j < (6 * i + 6) / 4; ++j)
+          *reinterpret_cast<float4*>(my + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       }
       if (a.traj) {
-#pragma unroll
-        for (int j = 0; j < PROP_CH * 6 / 4; ++j)
-          *reinterpret_cast<float4*>(s_trj + lane * PROP_TPITCH + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         __syncwarp();
-        // 32 candidates x 6 float4: per pass 8 candidates x 4 columns; 4 candidate groups x 2 column passes
-        // (columns 0-3, then 4-5 on the lower half-warp's column lanes)
+        float* dst0 = a.traj + (int64_t)t0 * a.t_cand + ch * (PROP_CH * 6);
+        if (cs == PROP_CH) {
+          // 32 candidates x 6 float4: per pass 8 candidates x columns 0-3, plus columns 4-5 on half the lanes
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cand = c8 + 8 * g;
-          if (cand < nb) {
-            float* dst = a.traj + (b0 + cand) * a.t_cand + (int64_t)ch * (PROP_CH * 6);
-            const float* src = s_trj + cand * PROP_TPITCH;
-            *(reinterpret_cast<float4*>(dst) + q4) = *reinterpret_cast<const float4*>(src + 4 * q4);
-            if (q4 < 2) *(reinterpret_cast<float4*>(dst) + 4 + q4) = *reinterpret_cast<const float4*>(src + 16 + 4 * q4);
+          for (int g = 0; g < 4; ++g) {
+            const int cand = c8 + 8 * g;
+            if (cand < nb) {
+              float* dst = dst0 + (int64_t)cand * a.t_cand;
+              const float* src = s_trj + cand * PROP_TPITCH;
+              PROP_ST(reinterpret_cast<float4*>(dst) + q4, *reinterpret_cast<const float4*>(src + 4 * q4));
+              if (q4 < 2) PROP_ST(reinterpret_cast<float4*>(dst) + 4 + q4, *reinterpret_cast<const float4*>(src + 16 + 4 * q4));
+            }
+          }
+        } else {  // ragged last chunk: cs * 3 float2 per candidate
+          const int per = cs * 3;
+          for (int idx = lane; idx < nb * per; idx += 32) {
+            const int cand = idx / per, k = idx - cand * per;
+            *(reinterpret_cast<float2*>(dst0 + (int64_t)cand * a.t_cand) + k) = *reinterpret_cast<const float2*>(s_trj + cand * PROP_TPITCH + 2 * k);
           }
         }
       }
       __syncwarp();
-    }
-    // tail steps (S not a multiple of PROP_CH): per-lane row accesses
-    for (int i = full * PROP_CH; i < a.S; ++i) {
-      if (live) {
-        float* o = a.traj ? a.traj + b * a.t_cand + (int64_t)i * 6 : nullptr;
-        if (e.alive) {
-          const float2 u = __ldg(reinterpret_cast<const float2*>(a.actions + b * a.a_cand + (int64_t)i * 2));
-          edge_step(c, e, i, u.x, u.y, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
-          if (o) {
-            *reinterpret_cast<float2*>(o) = make_float2(c.x, c.y);
-            *reinterpret_cast<float2*>(o + 2) = make_float2(c.psi, c.v);
-            *reinterpret_cast<float2*>(o + 4) = make_float2(c.D, c.dl);
-          }
-        } else if (o) {
-          *reinterpret_cast<float2*>(o) = make_float2(0.f, 0.f);
-          *reinterpret_cast<float2*>(o + 2) = make_float2(0.f, 0.f);
-          *reinterpret_cast<float2*>(o + 4) = make_float2(0.f, 0.f);
-        }
-      }
+      buf ^= 1;
     }
     if (live) {
+      const int64_t b = (int64_t)t0 + lane;
       if (a.state_out) {
-        float* so = a.state_out + b * a.s_cand;
-        so[0] = c.x; so[a.s_comp] = c.y; so[2 * a.s_comp] = c.psi; so[3 * a.s_comp] = c.v; so[4 * a.s_comp] = c.D;
-        so[5 * a.s_comp] = c.dl;
+        float* so = a.state_out + b * 6;
+        *reinterpret_cast<float2*>(so) = make_float2(c.x, c.y);
+        *reinterpret_cast<float2*>(so + 2) = make_float2(c.psi, c.v);
+        *reinterpret_cast<float2*>(so + 4) = make_float2(c.D, c.dl);
       }
       if (a.first_coll) a.first_coll[b] = e.first;
       if (a.done_step) a.done_step[b] = e.done;
     }
+    if (t0 + PROP_TSTRIDE < t0) break;  // 32-bit wrap
+    t0 += PROP_TSTRIDE;
   }
 }
 
@@ -291,32 +409,31 @@ extern "C" int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_
   const QMapView q = dt_qmap_view(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t map_smem = (size_t)m.bytes + (size_t)q.bytes;
-  // the reference's row layouts, 16-byte aligned: staged kernel
-  const bool rows = (a_comp == 1) && (a_step == 2) && (a_cand % 4 == 0) && (((uintptr_t)actions & 15) == 0) &&
+  // the reference's row layouts, 16-byte aligned rows: staged kernel
+  const bool rows = (B < (int64_t)0x7fffffff) && (s_cand == 6) && (s_comp == 1) && (((uintptr_t)state0 & 7) == 0) &&
+                    (!state_out || ((uintptr_t)state_out & 7) == 0) && (a_comp == 1) && (a_step == 2) &&
+                    (a_cand % 4 == 0) && (((uintptr_t)actions & 15) == 0) &&
                     (!traj_out || (t_comp == 1 && t_step == 6 && t_cand % 4 == 0 && ((uintptr_t)traj_out & 15) == 0));
   if (!ctx->prop_attr_set) {
-    DT_CUDA(cudaFuncSetAttribute(k_propagate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    DT_CUDA(cudaFuncSetAttribute(k_propagate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_propagate_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_propagate_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_propagate_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_propagate_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ctx->prop_attr_set = true;
   }
-  if (rows) {
-    const size_t smem = map_smem + (size_t)PROP_WARPS * PROP_STAGE_WORDS * sizeof(float);
-    int per_sm = 0;
-    DT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<true>, PROP_THREADS, smem));
-    if (per_sm < 1) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_propagate_collide: map too large for shared memory");
-    int64_t blocks = (B + PROP_THREADS - 1) / PROP_THREADS;
-    const int64_t cap = (int64_t)ctx->sm_count * per_sm;  // persistent: one wave of resident blocks
-    if (blocks > cap) blocks = cap;
-    k_propagate<true><<<(int)blocks, PROP_THREADS, smem, st>>>(m, q, a, ctx->d_status);
-  } else {
-    int per_sm = 0;
-    DT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<false>, PROP_THREADS, map_smem));
-    if (per_sm < 1) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_propagate_collide: map too large for shared memory");
-    int64_t blocks = (B + PROP_THREADS - 1) / PROP_THREADS;
-    const int64_t cap = (int64_t)ctx->sm_count * per_sm;
-    if (blocks > cap) blocks = cap;
-    k_propagate<false><<<(int)blocks, PROP_THREADS, map_smem, st>>>(m, q, a, ctx->d_status);
-  }
+  const bool table = q.g != nullptr;
+  const int threads = rows ? PROP_RTHREADS : PROP_THREADS;
+  const size_t smem = map_smem + (rows ? (size_t)PROP_RWARPS * PROP_WARP_WORDS * sizeof(float) : 0);
+  void (*kern)(MapView, QMapView, PropArgs, int*) =
+      rows ? (table ? k_propagate_rows<true> : k_propagate_rows<false>)
+           : (table ? k_propagate_strided<true> : k_propagate_strided<false>);
+  int per_sm = 0;
+  DT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_propagate_collide: map too large for shared memory");
+  int64_t blocks = (B + threads - 1) / threads;
+  const int64_t cap = (int64_t)ctx->sm_count * per_sm;  // persistent: one wave of resident blocks
+  if (blocks > cap) blocks = cap;
+  kern<<<(int)blocks, threads, smem, st>>>(m, q, a, ctx->d_status);
   DT_LAUNCH_CHECK("k_propagate");
   return DT_OK;
 }

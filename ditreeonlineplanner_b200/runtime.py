@@ -186,8 +186,14 @@ class Context:
             s_str = (6, 1)
             a_str = (act.stride(0), act.stride(1), 1)
             final = torch.empty_like(s0)
-            traj = torch.empty((B, S, 6), dtype=torch.float32, device=self.device) if want_traj else None
-            t_str = (S * 6, 6, 1)
+            # (B, S, 6) rows; the row pitch is padded to a whole number of 32-byte sectors so that every
+            # 4-step piece the kernel writes covers complete sectors (1200-byte rows would leave every other
+            # row straddling them: partial-sector writes cost L2 read-modify-writes)
+            pitch = -(-(S * 6) // 8) * 8
+            traj = None
+            if want_traj:
+                traj = torch.empty((B, pitch), dtype=torch.float32, device=self.device)[:, : S * 6].unflatten(1, (S, 6))
+            t_str = (pitch, 6, 1)
         first = torch.empty(B, dtype=torch.int32, device=self.device)
         done = torch.empty(B, dtype=torch.int32, device=self.device)
         self._check(self.lib.dt_propagate_collide(

@@ -16,7 +16,8 @@ ctx.set_map(grid)
 goal = goal_of(grid)
 S = 50
 ONLY = sys.argv[1] if len(sys.argv) > 1 else None   # e.g. "soa,no traj" : one config at B = 2^20 (for ncu)
-for B in ((1 << 20,) if ONLY else (4096, 1 << 16, 1 << 20, 1 << 22)):
+BS = [int(x) for x in os.environ["PROP_B"].split(",")] if os.environ.get("PROP_B") else None
+for B in (BS or ((1 << 20,) if ONLY else (4096, 1 << 16, 1 << 20, 1 << 22))):
     st_np, _ = synth_candidates(grid, B, 5)
     st = torch.as_tensor(st_np).cuda()
     act = torch.randn((B, S, 2), device="cuda") * torch.tensor([1.006, 0.923], device="cuda") + torch.tensor([0.451, 0.0], device="cuda")

@@ -366,10 +366,12 @@ def main():
     S = args.rollout
     bytes_edge = 4 * (2 * 6 + S * 2 + S * 6) + 8
     hbm = peaks.get("hbm_gbs", 6650.0)
-    prop = {"kernel": "k_propagate_collide", "bound": "hbm", "batch": Bp, "edges_per_s": Bp / (prop_ms * 1e-3),
+    prop = {"kernel": "k_propagate_rows (fused bicycle rollout + goal test + two-ball grid collision)", "bound": "hbm", "batch": Bp, "edges_per_s": Bp / (prop_ms * 1e-3),
             "achieved": Bp * bytes_edge / (prop_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
             "frac": Bp * bytes_edge / (prop_ms * 1e-3) / 1e9 / hbm, "bytes_per_edge": bytes_edge, "ms": prop_ms,
-            "note": "inputs (2^20 x 50 x 2 actions = 419 MB) and trajectory (1.26 GB) exceed the 126 MB L2"}
+            "note": "reference row layouts: states (B,6), actions (B,S,2), trajectory (B,S,6) with the row pitch padded "
+                    "to whole 32-byte sectors (1216 B for 1200 B of data; the padding is NOT counted as achieved "
+                    "bytes); inputs (419 MB) and trajectory (1.26 GB) exceed the 126 MB L2"}
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:

@@ -20,7 +20,7 @@
 
 #define PROP_THREADS 128
 #ifndef PROP_PF
-#define PROP_PF 1     // action prefetch distance of the strided kernel, steps (register ring)
+#define PROP_PF 2     // action prefetch distance of the strided kernel, steps (register ring)
 #endif
 // trajectory stores: never re-read by this kernel -> streaming (evict-first) stores
 #ifdef PROP_PLAIN_ST
@@ -149,8 +149,11 @@ __device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0,
 // ---------------------------------------------------------------------------------------------
 // Generic element strides (coalesced for struct-of-arrays buffers); next step's action prefetched
 // ---------------------------------------------------------------------------------------------
+#ifndef PROP_SMINB
+#define PROP_SMINB 5
+#endif
 template <bool kTable>
-__global__ void __launch_bounds__(PROP_THREADS, 6)
+__global__ void __launch_bounds__(PROP_THREADS, PROP_SMINB)
 k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   __shared__ uint64_t bar;

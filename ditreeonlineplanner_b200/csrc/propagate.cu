@@ -87,7 +87,7 @@ __device__ __forceinline__ void car_step(Car& c, float u0, float u1) {
 
 struct EdgeState {
   int first, done;
-  bool alive;
+  int alive;  // 0 / 1
 };
 
 // Rare path of a step, out of line: the heading left the MUFU range, a collision decision fell inside the
@@ -108,8 +108,8 @@ static __device__ __noinline__ float4 edge_slow(const uint8_t* __restrict__ grid
 }
 
 // one step of BasePlanner.propagate_action_sequence_env (planners/base_planner.py:281-317) for a live edge
-template <bool kTable>
-__device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0, float u1, bool stop,
+template <bool kTable, bool kStop>
+__device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0, float u1,
                                           const uint8_t* s_map, uint32_t s_q, const MapView& m, const QMapView& q,
                                           float gx, float gy, int* status) {
   car_step(c, u0, u1);
@@ -139,11 +139,14 @@ __device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0,
   }
   // collision ends the edge and the goal flag is then ignored (base_planner.py:306-312); goal reached: the
   // remaining actions are zeroed and the loop breaks (:314-317)
-  e.first = (coll & (e.first < 0)) ? i : e.first;
-  const bool die_c = coll & stop;
-  const bool die_g = in_goal & !die_c;
-  e.done = die_g ? i : e.done;
-  e.alive = !(die_c | die_g);
+  e.first = (coll && e.first < 0) ? i : e.first;
+  if (kStop) {
+    e.done = (in_goal && !coll) ? i : e.done;
+    e.alive = (coll || in_goal) ? 0 : 1;
+  } else {
+    e.done = in_goal ? i : e.done;
+    e.alive = in_goal ? 0 : 1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,7 +155,7 @@ __device__ __forceinline__ void edge_step(Car& c, EdgeState& e, int i, float u0,
 #ifndef PROP_SMINB
 #define PROP_SMINB 5
 #endif
-template <bool kTable>
+template <bool kTable, bool kStop>
 __global__ void __launch_bounds__(PROP_THREADS, PROP_SMINB)
 k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -161,7 +164,6 @@ k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status)
   uint32_t* s_qp = reinterpret_cast<uint32_t*>(s_dyn + m.bytes);
   dt_stage_maps(s_map, s_qp, &bar, m, q);
   const uint32_t s_q = dt_qmap_addr(s_qp, q);
-  const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
   for (int64_t b = blockIdx.x * (int64_t)PROP_THREADS + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * PROP_THREADS) {
     const float* s0 = a.state0 + b * a.s_cand;
     Car c;
@@ -170,7 +172,7 @@ k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status)
     dt_sincos_fast(c.psi, c.sn, c.cs);
     const float* act = a.actions + b * a.a_cand;
     float* tr = a.traj ? a.traj + b * a.t_cand : nullptr;
-    EdgeState e = {-1, -1, true};
+    EdgeState e = {-1, -1, 1};
     // actions are fetched PROP_PF steps ahead (register ring): under the trajectory's write traffic a
     // global load takes ~1 us, several steps of compute
     float n0[PROP_PF], n1[PROP_PF];
@@ -191,8 +193,8 @@ k_propagate_strided(MapView m, QMapView q, PropArgs a, int* __restrict__ status)
       }
       // one store per component for the whole warp (live lanes: the new state, finished lanes: zeros), so
       // a 128-byte line of a struct-of-arrays trajectory is written once, never as two partial writes
-      const bool was_alive = e.alive;
-      if (was_alive) edge_step<kTable>(c, e, i, u0, u1, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
+      const bool was_alive = e.alive != 0;
+      if (was_alive) edge_step<kTable, kStop>(c, e, i, u0, u1, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
       if (tr) {
         float* o = tr + i * a.t_step;
         PROP_ST(o, was_alive ? c.x : 0.f);
@@ -247,7 +249,7 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool kTable>
+template <bool kTable, bool kStop>
 __global__ void __launch_bounds__(PROP_RTHREADS, PROP_RMINB)
 k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -256,7 +258,6 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   uint32_t* s_qp = reinterpret_cast<uint32_t*>(s_dyn + m.bytes);
   dt_stage_maps(s_map, s_qp, &bar, m, q);
   const uint32_t s_q = dt_qmap_addr(s_qp, q);
-  const bool stop = (a.flags & DT_PROP_STOP_ON_COLLISION) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* s_warp = reinterpret_cast<float*>(s_dyn + m.bytes + q.bytes) + (size_t)warp * PROP_WARP_WORDS;
   float* s_act = s_warp;                          // 2 buffers of 32 x PROP_APITCH
@@ -310,7 +311,7 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   if (t0 < Bn && a.S > 0) issue(t0, 0, 0);
   int buf = 0;
   Car c = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
-  EdgeState e = {-1, -1, false};
+  EdgeState e = {-1, -1, 0};
   while (t0 < Bn) {
     const int nb = (int)((Bn - t0 < 32u) ? (Bn - t0) : 32u);
     const bool live = lane < nb;
@@ -325,7 +326,7 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
           c.x = p0.x; c.y = p0.y; c.psi = p1.x; c.v = p1.y; c.D = p2.x; c.dl = p2.y;
           dt_sincos_fast(c.psi, c.sn, c.cs);
         }
-        e.first = -1; e.done = -1; e.alive = live;
+        e.first = -1; e.done = -1; e.alive = live ? 1 : 0;
         __syncwarp();  // start states consumed before the next task's may land
       }
       // next chunk (possibly the next task's first) into the other buffer
@@ -339,7 +340,7 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
       for (int i = 0; i < PROP_CH; ++i) {
         if (e.alive && i < cs) {
           const float2 u = *reinterpret_cast<const float2*>(ua + 2 * i);
-          edge_step<kTable>(c, e, ch * PROP_CH + i, u.x, u.y, stop, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
+          edge_step<kTable, kStop>(c, e, ch * PROP_CH + i, u.x, u.y, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
           o[6 * i] = c.x; o[6 * i + 1] = c.y; o[6 * i + 2] = c.psi; o[6 * i + 3] = c.v; o[6 * i + 4] = c.D;
           o[6 * i + 5] = c.dl;
         } else {
@@ -417,19 +418,22 @@ extern "C" int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_
                     (!state_out || ((uintptr_t)state_out & 7) == 0) && (a_comp == 1) && (a_step == 2) &&
                     (a_cand % 4 == 0) && (((uintptr_t)actions & 15) == 0) &&
                     (!traj_out || (t_comp == 1 && t_step == 6 && t_cand % 4 == 0 && ((uintptr_t)traj_out & 15) == 0));
+  typedef void (*PropKernel)(MapView, QMapView, PropArgs, int*);
+  static const PropKernel kRowsK[2][2] = {{k_propagate_rows<false, false>, k_propagate_rows<false, true>},
+                                          {k_propagate_rows<true, false>, k_propagate_rows<true, true>}};
+  static const PropKernel kStridedK[2][2] = {{k_propagate_strided<false, false>, k_propagate_strided<false, true>},
+                                             {k_propagate_strided<true, false>, k_propagate_strided<true, true>}};
   if (!ctx->prop_attr_set) {
-    DT_CUDA(cudaFuncSetAttribute(k_propagate_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DT_CUDA(cudaFuncSetAttribute(k_propagate_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DT_CUDA(cudaFuncSetAttribute(k_propagate_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DT_CUDA(cudaFuncSetAttribute(k_propagate_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int i = 0; i < 4; ++i) {
+      DT_CUDA(cudaFuncSetAttribute(kRowsK[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      DT_CUDA(cudaFuncSetAttribute(kStridedK[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     ctx->prop_attr_set = true;
   }
-  const bool table = q.g != nullptr;
+  const int table = q.g != nullptr ? 1 : 0, stopf = (flags & DT_PROP_STOP_ON_COLLISION) ? 1 : 0;
   const int threads = rows ? PROP_RTHREADS : PROP_THREADS;
   const size_t smem = map_smem + (rows ? (size_t)PROP_RWARPS * PROP_WARP_WORDS * sizeof(float) : 0);
-  void (*kern)(MapView, QMapView, PropArgs, int*) =
-      rows ? (table ? k_propagate_rows<true> : k_propagate_rows<false>)
-           : (table ? k_propagate_strided<true> : k_propagate_strided<false>);
+  PropKernel kern = rows ? kRowsK[table][stopf] : kStridedK[table][stopf];
   int per_sm = 0;
   DT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_propagate_collide: map too large for shared memory");

@@ -6,8 +6,10 @@ test executed by the fused propagate+collide kernel.
 
 The scalar ``step`` costs one kernel launch; batched work goes through
 ``ditreeonlineplanner_b200.expansion.TreeExpander`` / ``BatchedCarEnv.step``.
-The probability-map sampler (run_type >= 2; prob_sampling_utils.py) is a "next" row of the scope
-table and is not implemented: constructing the env with run_type >= 2 raises NotImplementedError.
+run_type >= 2 (probability-map state sampling): ``prior`` is the normalised Euclidean distance transform of
+the free cells (``dt_edt_prior``), ``prob_map`` the prior (run_type 2) or its log-blend with a Gaussian along
+the robot -> goal line (run_type >= 3, ``dt_prob_map``), recomputed where the reference recomputes them
+(constructor, ``maze_map`` setter, ``update_prob_map_by_loc``; car_env.py:98-137).
 """
 from __future__ import annotations
 
@@ -46,8 +48,6 @@ class CarEnv:
     def __init__(self, lidar2dsim=None, dt=0.02, drone_radius=0.1, maze_map=None, collision_checking=True, run_type=0):
         if maze_map is None:
             raise ValueError("maze_map is required")
-        if run_type >= 2:
-            raise NotImplementedError("probability-map state sampling (run_type >= 2) is not on the B200 path yet")
         if lidar2dsim is None:
             from .lidar_sim.lidar_2d_sim import Lidar2DSim
             lidar2dsim = Lidar2DSim()
@@ -75,7 +75,14 @@ class CarEnv:
         self.done = False
         self.terminated = False
         self.run_type = run_type
-        self.prob_map = np.zeros_like(self._maze_map.copy())
+        self.gaussian_pdf = None
+        self._refresh_prior()
+        if self.run_type < 2:
+            self.prob_map = np.zeros_like(self._maze_map.copy())   # unused by the original / +reference runs
+        elif self.run_type == 2:
+            self.prob_map = self.prior
+        else:  # the constructor passes (row, col) un-swapped (car_env.py:107-109); the other call sites swap
+            self._blend(self.cell_xy_to_rowcol(self.state[:2]), self.cell_xy_to_rowcol(self.goal[:2]))
 
     # ---- map ------------------------------------------------------------------------------
     @property
@@ -86,6 +93,28 @@ class CarEnv:
     def maze_map(self, new_maze_map):
         self._maze_map = np.asarray(new_maze_map)
         invalidate_staged_map()
+        self._refresh_prior()
+        if self.run_type == 2:
+            self.prob_map = self.prior
+        elif self.run_type >= 3:
+            self.update_prob_map_by_loc()
+
+    # ---- probability-map sampler (car_env.py:98-137) ------------------------------------------
+    def _refresh_prior(self):
+        """prior = distance_transform_edt(1 - maze) / sum, on the device (skipped while nothing samples it)."""
+        if self.run_type < 2:
+            self.prior = None
+            return
+        self.prior = _ctx_for(self._maze_map, 1.0).edt_prior().cpu().numpy()
+
+    def _blend(self, robot, goal):
+        from .prob_sampling_utils import blended_prob_map
+        if tuple(self.prior.shape) != (20, 20):   # gaussian_map's default size (prob_sampling_utils.py:48)
+            raise ValueError(f"operands could not be broadcast together with shapes {self.prior.shape} (20,20)")
+        self.prob_map, self.gaussian_pdf = blended_prob_map(self.prior, robot, goal)
+
+    def update_prob_map_by_loc(self):
+        self._blend(self.cell_xy_to_rowcol(self.state[:2])[::-1], self.cell_xy_to_rowcol(self.goal[:2])[::-1])
 
     @property
     def maze_size_scaling(self):

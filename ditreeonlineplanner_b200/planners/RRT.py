@@ -64,8 +64,6 @@ class RRT_Planner(BasePlanner):
         self.plan_count = 0
         self.init_main_path = None
         self.run_type = kwargs.get("run_type", 0)
-        if self.run_type >= 2:
-            raise NotImplementedError("probability-map sampling (run_type >= 2) is a later row of the scope table")
         self.env.run_type = self.run_type
         self.batch_size = int(kwargs.get("batch_size", 1))
         self.iteration_cap = kwargs.get("iteration_cap", None)
@@ -147,6 +145,30 @@ class RRT_Planner(BasePlanner):
             return sample_node[0, :2] if random.random() > self.goal_conditioning_bias else self.goal_state[:2]
         return sample_node[0, :2]
 
+    def _sample_batch(self, B):
+        """B sampled states and their conditioning goals for one batched expansion round, vectorised: the
+        goal-bias coin, the cell draw (run_type >= 2: ONE device inverse-CDF search for all B uniform
+        variates) or the uniform position, and the four uniform state components of random_node_sample
+        (planners/base_planner.py:162-207); then the goal choice of RRT.py:154-157.  Same distributions as B
+        calls of the scalar path, different interleaving of the generator's stream."""
+        explore = np.random.random_sample(B) > self.goal_sample_rate
+        if self.run_type >= 2:
+            pm = np.asarray(self.env.prob_map, dtype=np.float64)
+            flat = _ctx_for(self.maze, self.s_global).sample_cells(pm, np.random.random_sample(B)).cpu().numpy()
+            rows, cols = np.unravel_index(flat, pm.shape)
+            xy = self.env.cell_rowcol_to_xy(np.array([rows, cols])).T
+        else:
+            xy = np.stack([np.random.uniform(-self.map_width / 2, self.map_width / 2, B),
+                           np.random.uniform(-self.map_length / 2, self.map_length / 2, B)], 1)
+        rest = np.stack([np.random.uniform(-np.pi, np.pi, B), np.random.uniform(-self.max_v, self.max_v, B),
+                         np.random.uniform(-1, 1, B), np.random.uniform(-0.40, 0.40, B)], 1)
+        samples = np.where(explore[:, None], np.concatenate([xy, rest], 1), np.asarray(self.goal_state, dtype=np.float64)[None])
+        goals = samples[:, :2].copy()
+        if self.run_type == 0:
+            to_goal = ~(np.random.random_sample(B) > self.goal_conditioning_bias)
+            goals[to_goal] = self.goal_state[:2]
+        return samples, goals.astype(np.float32)
+
     def _local_map(self, state):
         n = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
         self._ctx = _ctx_for(self.maze, self.s_global)
@@ -163,6 +185,8 @@ class RRT_Planner(BasePlanner):
         orig_prob_map = self.env.prob_map.copy()
         has_obstacle_ahead = []
         remain_init_path = None
+        if self.run_type >= 3:
+            self.env.update_prob_map_by_loc()
         if self.run_type > 0 and self.init_main_path is not None:
             remain_init_path = self.extract_path_after_obstacle()
         while (curr_time - start_time) < self.time_budget:
@@ -248,14 +272,15 @@ class RRT_Planner(BasePlanner):
         iter_num = 0
         has_obstacle_ahead = []
         orig_prob_map = self.env.prob_map.copy()
+        if self.run_type >= 3:
+            self.env.update_prob_map_by_loc()
         goal_xy = np.asarray(self.env.goal, dtype=np.float64)
         h = self.action_horizon
         while (time.time() - start_time) < self.time_budget:
             if self.iteration_cap is not None and iter_num >= self.iteration_cap:
                 break
-            samples = np.concatenate([self._sample_state(None) for _ in range(B)], axis=0)
+            samples, goals = self._sample_batch(B)
             parents = self.nearest_node_batch(samples)
-            goals = np.stack([self._pick_goal(samples[i:i + 1]) for i in range(B)]).astype(np.float32)
             for p in parents:
                 p.num_visit += 1
             edge_length = self.prop_duration_schedule[0]

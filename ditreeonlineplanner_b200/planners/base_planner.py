@@ -97,11 +97,29 @@ class BasePlanner(abc.ABC):
             return is_colliding_ant(state, self.maze, 1.2, self.s_global)
         raise NotImplementedError(self.env_id)
 
+    def sample_row_col_from_probability_map(self):
+        """np.random.choice(size, size=1, p=prob_map.ravel()) (base_planner.py:157-160): the one uniform
+        variate RandomState.choice consumes is drawn here, the inverse-CDF search runs on the device."""
+        pm = np.asarray(self.env.prob_map, dtype=np.float64)
+        s = pm.sum()
+        if not np.all(pm >= 0) or abs(s - 1.0) > 1.5e-8:   # NumPy's own checks (sqrt(eps) tolerance)
+            raise ValueError("probabilities do not sum to 1" if np.all(pm >= 0) else "probabilities are not non-negative")
+        u = np.random.random_sample(1)
+        flat = _ctx_for(self.maze, self.s_global).sample_cells(pm, u).cpu().numpy()
+        row, col = np.unravel_index(flat, pm.shape)
+        return row[np.newaxis], col[np.newaxis]
+
     def random_node_sample(self, batch_size=1):
-        """Same RNG consumption as the reference (python `random` then six np.random.uniform draws)."""
+        """Same RNG consumption as the reference (python `random`, then the cell draw or two uniform draws,
+        then four np.random.uniform draws)."""
         if random.random() > self.goal_sample_rate:
-            x = np.random.uniform(-self.map_width / 2, self.map_width / 2, size=(batch_size, 1))
-            y = np.random.uniform(-self.map_length / 2, self.map_length / 2, size=(batch_size, 1))
+            if getattr(self, "run_type", 0) >= 2:
+                rows, cols = self.sample_row_col_from_probability_map()
+                x, y = self.env.cell_rowcol_to_xy(np.array([rows[0], cols[0]]))
+                x, y = x[np.newaxis], y[np.newaxis]
+            else:
+                x = np.random.uniform(-self.map_width / 2, self.map_width / 2, size=(batch_size, 1))
+                y = np.random.uniform(-self.map_length / 2, self.map_length / 2, size=(batch_size, 1))
             theta = np.random.uniform(-np.pi, np.pi, size=(batch_size, 1))
             v = np.random.uniform(-self.max_v, self.max_v, size=(batch_size, 1))
             throttle = np.random.uniform(-1, 1, size=(batch_size, 1))

@@ -266,6 +266,41 @@ class Context:
                                             self._stream()))
         return u, amin, w
 
+    # -- probability-map state sampler (run_type >= 2) -----------------------------------------
+    def _f64(self, t):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t, dtype=np.float64))
+        if t.device != self.device or t.dtype != torch.float64:
+            t = t.to(self.device, torch.float64)
+        return t.contiguous()
+
+    def edt_prior(self):
+        """CarEnv.prior of the staged map: (rows, cols) float64 device tensor."""
+        out = torch.empty(tuple(self.map_shape), dtype=torch.float64, device=self.device)
+        self._check(self.lib.dt_edt_prior(self.h, _ptr(out), self._stream()))
+        return out
+
+    def prob_map(self, prior, robot_xy, goal_xy, beta=0.8):
+        """-> (prob_map, gaussian_pdf), both the prior's shape, float64 device tensors."""
+        pr = self._f64(prior)
+        assert pr.dim() == 2
+        out = torch.empty_like(pr)
+        gauss = torch.empty_like(pr)
+        rc = self.lib.dt_prob_map(self.h, pr.shape[0], pr.shape[1], _ptr(pr), float(robot_xy[0]), float(robot_xy[1]),
+                                  float(goal_xy[0]), float(goal_xy[1]), float(beta), _ptr(out), _ptr(gauss), self._stream())
+        if rc == L.DT_E_INDEX:
+            raise IndexError(self.lib.dt_last_error(self.h).decode())
+        self._check(rc)
+        return out, gauss
+
+    def sample_cells(self, prob, u):
+        """np.random.choice(prob.size, p=prob.ravel()) for the uniform draws u (B,) -> (B,) int32 flat indices."""
+        p = self._f64(prob).reshape(-1)
+        uu = self._f64(u).reshape(-1)
+        out = torch.empty(uu.shape[0], dtype=torch.int32, device=self.device)
+        self._check(self.lib.dt_sample_cells(self.h, _ptr(p), p.shape[0], _ptr(uu), uu.shape[0], _ptr(out), self._stream()))
+        return out
+
     # -- denoiser ---------------------------------------------------------------------------
     def load_denoiser(self, state_dict, action_dim, horizon, cond_dim, emb_dim, map_size, down_dims, max_batch):
         keep = []

@@ -140,6 +140,26 @@ int dt_goal_cost_argmin(dt_ctx* ctx, const float* node_x, const float* node_y, i
 int dt_mppi_reduce(dt_ctx* ctx, const float* cost, const float* noise, int64_t K, int TA, float lambda, float* u_inout,
                    int32_t* argmin_out, float* weights_out, void* stream);
 
+/* ---- probability-map state sampler (run_type >= 2) -------------------------------------------- */
+/* CarEnv.prior (car_env.py:100-101, maze_map setter :117-121): exact Euclidean distance transform of the
+ * free cells of the ctx map (scipy.ndimage.distance_transform_edt(1 - maze)) divided by its sum.
+ * prior_out: rows*cols float64, device. */
+int dt_edt_prior(dt_ctx* ctx, double* prior_out, void* stream);
+
+/* CarEnv.prob_map of run_type >= 3 (car_env.py:106-110,124-128,130-137): gaussian_map(robot, goal, size =
+ * (rows, cols)) (prob_sampling_utils.py:48-93) blended with the prior by combine_log_blend(prior, pdf, beta)
+ * (:150-172, eps = 1e-12, its fallbacks included).  robot / goal are the (x, y) pairs the reference passes
+ * (the pdf is zeroed at [int(robot_y), int(robot_x)]; DT_E_INDEX if that cell is outside the map, where
+ * NumPy raises).  prior, prob_out, gauss_out: rows*cols float64, device; gauss_out receives CarEnv.gaussian_pdf. */
+int dt_prob_map(dt_ctx* ctx, int rows, int cols, const double* prior, double robot_x, double robot_y, double goal_x,
+                double goal_y, double beta, double* prob_out, double* gauss_out, void* stream);
+
+/* BasePlanner.sample_row_col_from_probability_map (planners/base_planner.py:157-160) for B draws:
+ * np.random.choice(n, p = prob) is cdf = cumsum(prob); cdf /= cdf[-1]; searchsorted(cdf, u, side='right') with
+ * u ~ U[0,1) from the caller's generator; idx_out[b] is the flat cell index (bit-exact vs NumPy for the same u).
+ * prob (n) f64, u (B) f64, idx_out (B) i32, all device. */
+int dt_sample_cells(dt_ctx* ctx, const double* prob, int n, const double* u, int64_t B, int32_t* idx_out, void* stream);
+
 /* ---- denoiser (local_map_encoder.py:78-122, conditional_unet1d.py:268-347, fm_policy.py:152-203) */
 typedef struct {
   const char* name;   /* reference state_dict key, e.g. "unet.mid_modules.0.blocks.0.block.0.weight" */

@@ -508,3 +508,71 @@ def mppi_reduce(cost, noise, lam, u):
     w = w / w.sum()
     u_new = np.asarray(u, dtype=np.float64) + np.tensordot(w, np.asarray(noise, dtype=np.float64), axes=(0, 0))
     return u_new, int(np.argmin(c)), w
+
+
+# ---------------------------------------------------------------------------------------------
+# probability-map state sampler (run_type >= 2)
+# ---------------------------------------------------------------------------------------------
+def edt_prior(grid):
+    """CarEnv.prior (car_env.py:100-101): distance_transform_edt(1 - maze) / sum, by exhaustive search.
+    The exact transform is the square root of an integer squared distance, so this matches SciPy's
+    float64 values bit for bit on any map that has a wall cell (SciPy itself is not used: the oracle must
+    not depend on which SciPy the GPU box carries)."""
+    g = np.asarray(grid)
+    rows, cols = g.shape
+    fg = g != 1                      # non-zero entries of 1 - maze
+    wr, wc = np.nonzero(~fg)
+    rr, cc = np.mgrid[0:rows, 0:cols]
+    if len(wr) == 0:                 # SciPy's result without any background cell (never the case in the data)
+        d2 = (rr + 1) ** 2 + cc ** 2
+    else:
+        d2 = ((rr[..., None] - wr) ** 2 + (cc[..., None] - wc) ** 2).min(axis=-1)
+    edt = np.sqrt(d2.astype(np.float64)) * fg
+    return edt / np.sum(edt)
+
+
+def gaussian_map(robot, goal, size=(20, 20)):
+    """prob_sampling_utils.py:48-93: a discrete 2-D Gaussian elongated along robot -> goal; the mean slides
+    from the goal (near) to the midpoint (far); zero at the robot's own cell; normalised."""
+    H, W = size
+    rx, ry = float(robot[0]), float(robot[1])
+    gx, gy = float(goal[0]), float(goal[1])
+    dx, dy = gx - rx, gy - ry
+    d = np.sqrt(dx ** 2 + dy ** 2) + 1e-6
+    u = np.array([dx, dy]) / d if d > 1e-6 else np.array([1.0, 0.0])
+    v = np.array([-u[1], u[0]])
+    mid = np.array([(rx + gx) / 2, (ry + gy) / 2])
+    w = -np.exp(-d / 15) + 1
+    mean = (1 - w) * np.array([gx, gy]) + w * mid
+    s_long = 1.0 + 0.7 * np.log1p(d)
+    s_side = 0.7 * s_long
+    rot = np.stack([u, v], axis=1)
+    sigma = rot @ np.diag([s_long ** 2, s_side ** 2]) @ rot.T
+    inv = np.linalg.inv(sigma)
+    ys, xs = np.mgrid[0:H, 0:W]
+    diff = np.stack([xs, ys], axis=-1) - mean
+    expo = np.sum((diff @ inv) * diff, axis=2)
+    pdf = np.exp(-0.5 * expo)
+    pdf[int(ry), int(rx)] = 0
+    return pdf / pdf.sum()
+
+
+def combine_log_blend(prior, gauss, beta=0.8, eps=1e-12):
+    """prob_sampling_utils.py:150-172 without an obstacle mask (the reference never passes one)."""
+    post = np.exp(beta * np.log(prior + eps) + (1.0 - beta) * np.log(gauss + eps)) * (prior > 0)
+    s = post.sum()
+    if s <= eps:
+        post = prior.copy()
+        s = post.sum()
+        if s <= eps:
+            post = np.ones_like(post)
+            s = post.sum()
+    return post / s
+
+
+def sample_cells(prob, u):
+    """np.random.choice(prob.size, p=prob.ravel()) for given uniform draws (legacy RandomState.choice):
+    cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')."""
+    cdf = np.cumsum(np.asarray(prob, dtype=np.float64).ravel())
+    cdf /= cdf[-1]
+    return cdf.searchsorted(np.asarray(u, dtype=np.float64), side="right")

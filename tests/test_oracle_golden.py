@@ -204,3 +204,19 @@ def test_mppi_reduce_properties():
     assert amin == int(np.argmin(cost)) and abs(w.sum() - 1) < 1e-12
     u2, _, _ = orc.mppi_reduce(cost + 100.0, noise, 0.5, np.zeros((16, 2)))
     np.testing.assert_allclose(u, u2, rtol=1e-9)  # shift invariance
+
+
+# ---- probability-map state sampler (run_type >= 2) ---------------------------------------------
+def test_probmap_oracle(mazes):
+    g = golden("probmap.npz")
+    for m in MAZES:
+        assert np.array_equal(orc.edt_prior(mazes[m]), g[f"{m}.prior"])          # exact: sqrt of integer d^2
+    free = np.zeros((4, 5))
+    want = np.sqrt((np.arange(4)[:, None] + 1.0) ** 2 + np.arange(5)[None, :] ** 2)   # SciPy on a wall-free map
+    np.testing.assert_allclose(orc.edt_prior(free), want / want.sum(), rtol=1e-15)
+    for i in range(int(g["n_cases"])):
+        pdf = orc.gaussian_map(g[f"{i}.robot"], g[f"{i}.goal"])
+        np.testing.assert_allclose(pdf, g[f"{i}.pdf"], rtol=1e-13, atol=1e-300)
+        blend = orc.combine_log_blend(g[f"{str(g[f'{i}.maze'])}.prior"], g[f"{i}.pdf"])
+        np.testing.assert_allclose(blend, g[f"{i}.blend"], rtol=1e-13, atol=1e-300)
+        assert np.array_equal(orc.sample_cells(g[f"{i}.blend"], g[f"{i}.u"]), g[f"{i}.idx"])

@@ -485,12 +485,60 @@ def gen_tree():
          actions=np.zeros((0, 2), np.float32) if actions is None else actions)
 
 
+def gen_probmap():
+    """run_type >= 2 sampler: SciPy EDT prior on every maze, gaussian_map + combine_log_blend for seeded
+    (robot, goal) pairs on the 20 x 20 mazes, and np.random.choice draws with the uniform variates that
+    produced them (RandomState.choice consumes exactly one random_sample per draw)."""
+    from scipy.ndimage import distance_transform_edt
+    import prob_sampling_utils as psu
+    out = {}
+    for m in MAZES:
+        maze = load_maze(m)
+        pr = distance_transform_edt(1 - maze)
+        out[f"{m}.prior"] = pr / np.sum(pr)
+    rng = np.random.default_rng(5)
+    cases = []
+    for m in ("boxes",):
+        maze = load_maze(m)
+        assert maze.shape == (20, 20)
+        prior = out[f"{m}.prior"]
+        for k in range(24):
+            robot = rng.uniform(0, 20, 2)
+            goal = rng.uniform(0, 20, 2) if k else robot.copy()   # k = 0: robot == goal (degenerate direction)
+            pdf, _, _ = psu.gaussian_map(robot, goal)
+            blend = psu.combine_log_blend(prior, pdf)
+            np.random.seed(100 + k)
+            st = np.random.get_state()
+            idx = np.array([int(np.random.choice(blend.size, size=1, p=blend.ravel())[0]) for _ in range(64)])
+            np.random.set_state(st)
+            u = np.random.random_sample(64)
+            cases.append((m, robot, goal, pdf, blend, idx, u))
+    out["n_cases"] = np.array(len(cases))
+    for i, (m, robot, goal, pdf, blend, idx, u) in enumerate(cases):
+        out[f"{i}.maze"] = np.array(m)
+        out[f"{i}.robot"], out[f"{i}.goal"], out[f"{i}.pdf"], out[f"{i}.blend"] = robot, goal, pdf, blend
+        out[f"{i}.idx"], out[f"{i}.u"] = idx, u
+    # CarEnv itself with run_type 2 / 3: constructor, maze_map setter, update_prob_map_by_loc
+    maze = load_maze("boxes")
+    env = car_env.CarEnv(maze_map=maze.copy(), collision_checking=False, run_type=3)
+    out["env.init_prob"] = env.prob_map.copy()
+    env.reset(options={"reset_cell": np.array([12, 15]), "reset_deg": 90.0, "goal_cell": np.array([2, 17])})
+    env.update_prob_map_by_loc()
+    out["env.loc_prob"], out["env.state"], out["env.goal"] = env.prob_map.copy(), env.state.copy(), np.asarray(env.goal, float)
+    maze2 = insert_box(maze.copy(), 10, 15, 1, 4)
+    env.maze_map = maze2
+    out["env.setter_prob"], out["env.setter_prior"] = env.prob_map.copy(), env.prior.copy()
+    env2 = car_env.CarEnv(maze_map=maze.copy(), collision_checking=False, run_type=2)
+    out["env2.prob"] = env2.prob_map.copy()
+    save("probmap.npz", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["data", "schedule", "local_map", "collide_car", "collide_ant", "bicycle", "propagate",
-                             "cond", "denoiser", "lidar", "probe", "tree"]
+                             "cond", "denoiser", "lidar", "probe", "tree", "probmap"]
     fns = dict(data=gen_data_fixtures, schedule=gen_schedule, local_map=gen_local_map, collide_car=gen_collide_car,
                collide_ant=gen_collide_ant, bicycle=gen_bicycle, propagate=gen_propagate, cond=gen_cond,
-               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, tree=gen_tree)
+               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, tree=gen_tree, probmap=gen_probmap)
     for w in which:
         print(f"[{w}]")
         fns[w]()

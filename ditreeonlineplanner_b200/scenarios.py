@@ -114,3 +114,93 @@ def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car",
     local = [unit_fn(rows[s], s, r, sampler, time_budget, planner_kwargs) for s, r in mine]
     table = gather_rows(mine, local, len(rows) * total_runs, device, world)
     return table, time.time() - t0
+
+
+# ---------------------------------------------------------------------------------------------
+# wire formats
+# ---------------------------------------------------------------------------------------------
+# The reference's per-scenario CSV (run_scenarios.py:331-333,392-395): the header names TEN columns but every
+# row carries ELEVEN values (trajectory_time sits between trajectory_length and avg_velocity without a
+# header cell).  results_process.py reads these files with pandas, so the quirk is kept byte for byte.
+CSV_HEADER = ["iteration", "success", "runtime", "trajectory_length", "avg_velocity", "num_states_in_tree",
+              "num_RRT_iterations", "ctrl_effort_max", "ctrl_effort_mean", "ctrl_effort_std"]
+
+
+def scenario_csv_path(root, current_run, scenario_name, planner_name="diffusion_RRT_PD64", env_id="carmaze"):
+    """benchmark_results/{current_run}/{scenario}_{planner}_{env_id}.csv (run_scenarios.py:306)."""
+    import os
+    return os.path.join(root, "benchmark_results", str(current_run), f"{scenario_name}_{planner_name}_{env_id}.csv")
+
+
+def next_run_index(root):
+    """The reference numbers result directories 1, 2, ... (run_scenarios.py:191-195)."""
+    import os
+    d = os.path.join(root, "benchmark_results")
+    os.makedirs(d, exist_ok=True)
+    taken = [int(x) for x in os.listdir(d) if x.isdigit()]
+    return max(taken) + 1 if taken else 1
+
+
+def existing_rows(path):
+    """Rows already present (header excluded): the reference resumes a scenario file where it stopped
+    (run_scenarios.py:308-323)."""
+    import csv
+    import os
+    if not os.path.exists(path):
+        return 0
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    return len(rows) - 1 if len(rows) > 1 else 0
+
+
+def write_suite_csv(table, root, current_run=None, kind="test_scenarios_car", planner_name="diffusion_RRT_PD64",
+                    env_id="carmaze"):
+    """Write the gathered result table ({(scenario, run): row}) as the reference's per-scenario CSV files.
+    Integer-valued fields the reference writes as Python ints (iteration, success, the -1 / 0 sentinels,
+    node and iteration counts) are written as ints.  -> list of paths."""
+    import csv
+    import os
+    rows = load_scenarios(kind)
+    current_run = next_run_index(root) if current_run is None else current_run
+    paths = []
+    for s_idx, sc_row in enumerate(rows):
+        mine = sorted((r, v) for (s, r), v in table.items() if s == s_idx)
+        if not mine:
+            continue
+        path = scenario_csv_path(root, current_run, sc_row["scenario_name"], planner_name, env_id)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        have = existing_rows(path)
+        if have == 0:
+            with open(path, "w", newline="") as f:
+                csv.writer(f).writerow(CSV_HEADER)
+        with open(path, "a", newline="") as f:
+            w = csv.writer(f)
+            for r, v in mine:
+                if r < have:
+                    continue
+                it, ok, runtime, length, ttime, vel, nodes, iters, emax, emean, estd = v
+                ok = int(ok)
+                sent = (lambda x: int(x) if float(x) in (-1.0, 0.0) else float(x))
+                w.writerow([int(it), ok, float(runtime), float(length) if ok == 1 else sent(length),
+                            float(ttime) if ok == 1 else sent(ttime), float(vel) if ok == 1 else sent(vel),
+                            int(nodes), int(iters), float(emax) if ok == 1 else sent(emax),
+                            float(emean) if ok == 1 else sent(emean), float(estd) if ok == 1 else sent(estd)])
+        paths.append(path)
+    return paths
+
+
+def save_path_csv(path_array, filename):
+    """np.savetxt(f'path_DP_{i}.csv', path_array, fmt='%.6f', delimiter=',') (run_scenarios.py:352)."""
+    np.savetxt(filename, np.asarray(path_array), fmt="%.6f", delimiter=",")
+
+
+def load_checkpoint_state_dict(path, map_location="cpu"):
+    """The reference's training checkpoint (run_scenarios.py:175-176): a torch file whose
+    'noise_pred_net_state_dict' entry is the ConditionalUnet1DWithLocalMap state_dict; its keys are exactly the
+    names ``dt_load_denoiser`` expects, so the result feeds ``DiffusionSampler`` / ``Context.load_denoiser``
+    unchanged.  A bare state_dict file is accepted too."""
+    ck = torch.load(path, map_location=map_location, weights_only=True)
+    sd = ck.get("noise_pred_net_state_dict", ck) if isinstance(ck, dict) else ck
+    if not isinstance(sd, dict) or not any(k.startswith("unet.") for k in sd):
+        raise KeyError("checkpoint holds no 'noise_pred_net_state_dict' of the reference architecture")
+    return {k: v.float() for k, v in sd.items()}

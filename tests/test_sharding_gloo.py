@@ -70,3 +70,47 @@ def test_result_row_schema():
     row = sc.result_row(0, path, acts, {"path_time": 0.06, "number_of_nodes": 3, "iterations": 16}, 1.5)
     assert len(row) == 11 and row[1] == 1 and abs(row[3] - 2.0) < 1e-6 and row[8] == 2.0
     assert sc.result_row(4, None, None, {"iterations": 7, "number_of_nodes": 2}, 0.5)[:2] == [5, 0]
+
+
+def test_reference_csv_wire_format(tmp_path):
+    """The per-scenario CSV the reference writes (run_scenarios.py:331-333,392-395): 10 header cells, 11 values
+    per row, ints for counters / sentinels, append-resume; readable the way results_process.py reads it."""
+    import csv
+    from ditreeonlineplanner_b200 import scenarios as sc
+    from ditreeonlineplanner_b200.data import load_scenarios
+    rows = load_scenarios("test_scenarios_car")
+    ok = sc.result_row(0, np.array([[0, 0, 1.0, 0.5, 0, 0], [3, 4, 1.0, 0.5, 0, 0]], float), np.array([[3.0, 4.0], [0.0, 1.0]]),
+                       {"number_of_nodes": 17, "iterations": 285, "path_time": 1.28}, 2.5)
+    fail = sc.result_row(1, None, None, {"number_of_nodes": 40, "iterations": 300}, 4.0)
+    table = {(0, 0): ok, (0, 1): fail, (3, 0): ok}
+    paths = sc.write_suite_csv(table, str(tmp_path), current_run=1)
+    assert [p.split("/")[-1] for p in paths] == [f"{rows[0]['scenario_name']}_diffusion_RRT_PD64_carmaze.csv",
+                                                 f"{rows[3]['scenario_name']}_diffusion_RRT_PD64_carmaze.csv"]
+    with open(paths[0], newline="") as f:
+        lines = list(csv.reader(f))
+    assert lines[0] == ["iteration", "success", "runtime", "trajectory_length", "avg_velocity", "num_states_in_tree",
+                        "num_RRT_iterations", "ctrl_effort_max", "ctrl_effort_mean", "ctrl_effort_std"]
+    assert len(lines) == 3 and all(len(r) == 11 for r in lines[1:])
+    assert lines[1][:2] == ["1", "1"] and float(lines[1][3]) == 5.0 and lines[1][6:8] == ["17", "285"]
+    assert lines[2] == ["2", "0", "4.0", "-1", "0", "-1", "-1", "300", "-1", "-1", "-1"]   # the reference's failure row
+    # resume: rows already present are not rewritten, new runs are appended
+    table[(0, 2)] = sc.result_row(2, None, None, {"number_of_nodes": 1, "iterations": 5}, 1.0)
+    sc.write_suite_csv(table, str(tmp_path), current_run=1)
+    assert sc.existing_rows(paths[0]) == 3
+    assert sc.next_run_index(str(tmp_path)) == 2
+    sc.save_path_csv(np.array([[1.0, 2.5], [3.25, -4.0]]), str(tmp_path / "path_DP_0.csv"))
+    assert open(tmp_path / "path_DP_0.csv").read() == "1.000000,2.500000\n3.250000,-4.000000\n"
+
+
+def test_checkpoint_loader(tmp_path):
+    import torch
+    from oracle import denoiser_ref as dref
+    from ditreeonlineplanner_b200 import scenarios as sc
+    sd = dref.init_params(seed=1, input_dim=2, cond_dim=7, emb_dim=400, down_dims=[64, 128, 256])
+    torch.save({"noise_pred_net_state_dict": sd, "epoch": 3, "optimizer_state_dict": {}}, tmp_path / "ck.pt")
+    got = sc.load_checkpoint_state_dict(str(tmp_path / "ck.pt"))
+    assert set(got) == set(sd) and all(torch.equal(got[k], torch.as_tensor(sd[k]).float()) for k in sd)
+    torch.save({"something": torch.zeros(1)}, tmp_path / "bad.pt")
+    import pytest
+    with pytest.raises(KeyError):
+        sc.load_checkpoint_state_dict(str(tmp_path / "bad.pt"))

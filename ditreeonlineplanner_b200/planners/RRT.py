@@ -268,7 +268,7 @@ class RRT_Planner(BasePlanner):
         self._ctx = _ctx_for(self.maze, self.s_global)
         exp = TreeExpander(ctx, smp.metadata, n_map, self.local_map_scale, num_diffusion_iters=smp.num_diffusion_iters,
                            pred_horizon=smp.pred_horizon, action_horizon=self.action_horizon, action_dim=smp.action_dim)
-        mean = torch.as_tensor(smp.metadata["Actions_mean"].astype(np.float32), device=ctx.device)
+        mean_np = smp.metadata["Actions_mean"].astype(np.float32)
         iter_num = 0
         has_obstacle_ahead = []
         orig_prob_map = self.env.prob_map.copy()
@@ -284,18 +284,23 @@ class RRT_Planner(BasePlanner):
             for p in parents:
                 p.num_visit += 1
             edge_length = self.prop_duration_schedule[0]
-            states = torch.as_tensor(np.stack([p.state for p in parents]).astype(np.float32), device=ctx.device)
+            n_chunks = edge_length // h
+            states = torch.as_tensor(np.stack([p.state for p in parents]).astype(np.float32)).to(ctx.device, non_blocking=True)
             # previous action = last action of the parent's edge; roots have none -> the action mean, whose
             # normalised value is 0, which is what the reference feeds for prev_actions=None
-            prev = torch.stack([mean if p.parent_action_seq is None or len(p.parent_action_seq) == 0 else
-                                torch.as_tensor(np.asarray(p.parent_action_seq[-1], dtype=np.float32), device=ctx.device)
-                                for p in parents])
-            goals_d = torch.as_tensor(goals, device=ctx.device)
+            prev_np = np.stack([mean_np if p.parent_action_seq is None or len(p.parent_action_seq) == 0 else
+                                np.asarray(p.parent_action_seq[-1], dtype=np.float32) for p in parents])
+            prev = torch.as_tensor(prev_np).to(ctx.device, non_blocking=True)
+            goals_d = torch.as_tensor(goals).to(ctx.device, non_blocking=True)
             alive = torch.ones(B, dtype=torch.bool, device=ctx.device)
             reached = torch.zeros(B, dtype=torch.bool, device=ctx.device)
-            chunks = []  # per chunk: (start states, actions, trajectory, took-part mask, steps taken)
-            for _ in range(edge_length // h):
-                iter_num += int(alive.sum())
+            n_iter = torch.zeros((), dtype=torch.int64, device=ctx.device)
+            c_s0, c_a, c_t, c_m, c_n = [], [], [], [], []
+            # The whole edge is enqueued without a host-device synchronisation: candidates whose edge already
+            # ended (collision / goal) ride along masked out, which costs nothing extra on the device (the
+            # batch is processed as a whole either way) and lets the host run ahead of the GPU.
+            for _ in range(n_chunks):
+                n_iter += alive.sum()
                 lm = ctx.local_map(states, n_map, self.local_map_scale, bf16_signed=True)
                 cond = ctx.build_cond_car(states, prev, goals_d, smp.metadata, float(n_map))
                 noise = torch.randn((B, smp.pred_horizon, smp.action_dim), device=ctx.device)
@@ -306,29 +311,31 @@ class RRT_Planner(BasePlanner):
                 done = res["done_step"] >= 0
                 took = alive & ~coll                      # candidates whose chunk is kept
                 steps = torch.where(done, res["done_step"] + 1, torch.full_like(res["done_step"], h))
-                chunks.append((states, a[:, :h], res["traj"], took, steps))
+                c_s0.append(states); c_a.append(a[:, :h]); c_t.append(res["traj"]); c_m.append(took); c_n.append(steps)
                 reached = reached | (took & done)
                 alive = took & ~done                      # a collision drops the whole edge (RRT.py:179-184)
                 states = torch.where(took[:, None], res["final"], states)
                 prev = torch.where(took[:, None], a[:, h - 1], prev)
-                if not bool(alive.any()):
-                    break
+            # one round trip per round: five stacked arrays instead of one copy per chunk and tensor
             ok = (alive | reached).cpu().numpy()
+            iter_num += int(n_iter.item())
             if ok.any():
                 reached_h = reached.cpu().numpy()
                 fin = states.cpu().numpy().astype(np.float64)
-                host = [(s0.cpu().numpy().astype(np.float64), a.cpu().numpy().astype(np.float64),
-                         t.cpu().numpy().astype(np.float64), m.cpu().numpy(), n.cpu().numpy())
-                        for s0, a, t, m, n in chunks]
+                S0 = torch.stack(c_s0).cpu().numpy().astype(np.float64)          # (chunks, B, 6)
+                A = torch.stack(c_a).cpu().numpy().astype(np.float64)            # (chunks, B, h, 2)
+                T = torch.stack(c_t).cpu().numpy().astype(np.float64)            # (chunks, B, h, 6)
+                M = torch.stack(c_m).cpu().numpy()
+                N = torch.stack(c_n).cpu().numpy()
                 for b in np.nonzero(ok)[0]:
                     a_seq, s_seq = [], []
-                    for s0, a_np, t_np, m_np, n_np in host:
-                        if not m_np[b]:
+                    for c in range(n_chunks):
+                        if not M[c, b]:
                             break
-                        n = int(n_np[b])
-                        a_seq.append(a_np[b, :n])
-                        s_seq.append(s0[b][None])          # every chunk starts with its start state,
-                        s_seq.append(t_np[b, :n])          # like the reference's states_sequence
+                        n = int(N[c, b])
+                        a_seq.append(A[c, b, :n])
+                        s_seq.append(S0[c, b][None])       # every chunk starts with its start state,
+                        s_seq.append(T[c, b, :n])          # like the reference's states_sequence
                         if n < h:
                             break
                     node = Node(fin[b], np.concatenate(a_seq), np.concatenate(s_seq)[None], parent=parents[b])

@@ -337,3 +337,43 @@ def test_lidar_batch_vs_oracle(ctx):
         d, e, v = orc.lidar_scan(poses[b].astype(np.float64), maze.astype(np.float64))
         np.testing.assert_allclose(dist[b].cpu().numpy(), d, rtol=0, atol=1e-5)
         assert np.array_equal(np.floor(end[b].cpu().numpy()), np.floor(e))
+
+
+def test_propagate_full_size_properties(ctx, mazes):
+    """BASELINE-size batch (2^20 candidates x 50 steps, 1.7 GB of traffic): size-independent properties.
+    (1) a candidate's result does not depend on its position in the batch (permutation invariance),
+    (2) the row and struct-of-arrays kernels give the same bits, (3) a strided sample of edges is
+    teacher-forced against the oracle (flags bit-exact), (4) rows past the end of an edge are zero."""
+    grid = mazes["boxes"]
+    ctx.set_map(grid)
+    rng = np.random.default_rng(99)
+    B, S = 1 << 20, 50
+    free = np.argwhere(grid == 0)
+    cells = free[rng.integers(0, len(free), B)]
+    x, y = orc.rowcol_to_xy(cells[:, 0], cells[:, 1], grid.shape)
+    s0 = np.stack([x + rng.uniform(-0.3, 0.3, B), y + rng.uniform(-0.3, 0.3, B), rng.uniform(-np.pi, np.pi, B),
+                   rng.uniform(0, 4, B), rng.uniform(0, 1.3, B), rng.uniform(-0.44, 0.44, B)], 1).astype(np.float32)
+    act = torch.randn((B, S, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * \
+        torch.tensor([1.0, 0.92], device="cuda") + torch.tensor([0.45, 0.0], device="cuda")
+    goal = (7.5, 7.5)
+    st = dev(s0)
+    res = ctx.propagate_collide(st, act, goal)
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    res_p = ctx.propagate_collide(st[perm].contiguous(), act[perm].contiguous(), goal)
+    for k in ("final", "first_coll", "done_step"):
+        assert torch.equal(res[k][perm], res_p[k]), k
+    assert torch.equal(res["traj"][perm[:4096]], res_p["traj"][:4096])
+    soa = ctx.propagate_collide(st.t().contiguous(), act.permute(1, 2, 0).contiguous(), goal, soa=True, want_traj=False)
+    assert torch.equal(soa["final"].t(), res["final"])
+    assert torch.equal(soa["first_coll"], res["first_coll"]) and torch.equal(soa["done_step"], res["done_step"])
+    sel = np.arange(0, B, 53)
+    traj = res["traj"][torch.as_tensor(sel, device="cuda")].cpu().numpy()
+    forced = orc.rollout_car(s0[sel], act[torch.as_tensor(sel, device="cuda")].cpu().numpy(), goal, grid, states_for_flags=traj)
+    first = res["first_coll"].cpu().numpy()[sel]
+    done = res["done_step"].cpu().numpy()[sel]
+    assert np.array_equal(first, forced["first_coll"]) and np.array_equal(done, forced["done_step"])
+    end = np.where(first >= 0, first, np.where(done >= 0, done, S - 1))
+    for i in range(0, len(sel), 101):
+        assert np.all(traj[i, end[i] + 1:] == 0)
+    frac_coll = float((res["first_coll"] >= 0).float().mean())
+    assert 0.2 < frac_coll < 0.9

@@ -95,6 +95,15 @@ class RRT_Planner(BasePlanner):
         self.node_list.append(node)
         self._tree.append(np.asarray(node.state[:2]))
 
+    def _insert_many(self, nodes):
+        """One device append for a whole round of new nodes (the batched planner)."""
+        if not nodes:
+            return
+        for node in nodes:
+            node.index = len(self.node_list)
+            self.node_list.append(node)
+        self._tree.append(np.stack([np.asarray(n.state[:2]) for n in nodes]))
+
     def nearest_node(self, sample):
         idx = self._ctx.nearest(self._tree.x[:self._tree.n], self._tree.y[:self._tree.n],
                                 torch.as_tensor(np.asarray(sample, dtype=np.float32)[:, :2]))
@@ -327,6 +336,7 @@ class RRT_Planner(BasePlanner):
                 T = torch.stack(c_t).cpu().numpy().astype(np.float64)            # (chunks, B, h, 6)
                 M = torch.stack(c_m).cpu().numpy()
                 N = torch.stack(c_n).cpu().numpy()
+                new_nodes, goal_node = [], None
                 for b in np.nonzero(ok)[0]:
                     a_seq, s_seq = [], []
                     for c in range(n_chunks):
@@ -339,9 +349,16 @@ class RRT_Planner(BasePlanner):
                         if n < h:
                             break
                     node = Node(fin[b], np.concatenate(a_seq), np.concatenate(s_seq)[None], parent=parents[b])
-                    self._insert(node)
-                    has_obstacle_ahead.append(False if self.run_type == 0 else self.check_obstacle_ahead(fin[b]))
+                    new_nodes.append(node)
                     if reached_h[b]:
-                        self.env.prob_map = orig_prob_map
-                        return self.handle_goal_reached(node, iter_num, start_time)
+                        goal_node = node
+                        break
+                self._insert_many(new_nodes)
+                if self.run_type == 0:
+                    has_obstacle_ahead.extend([False] * len(new_nodes))
+                else:
+                    has_obstacle_ahead.extend(self.check_obstacle_ahead(n.state) for n in new_nodes)
+                if goal_node is not None:
+                    self.env.prob_map = orig_prob_map
+                    return self.handle_goal_reached(goal_node, iter_num, start_time)
         return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)

@@ -67,6 +67,11 @@ class RRT_Planner(BasePlanner):
         self.env.run_type = self.run_type
         self.batch_size = int(kwargs.get("batch_size", 1))
         self.iteration_cap = kwargs.get("iteration_cap", None)
+        # batched expansion flavour: "continuous" refills a slot as soon as its edge ends (every slot does
+        # useful work in every device pass); "rounds" expands one batch of edges to completion at a time
+        self.batch_mode = kwargs.get("batch_mode", "continuous")
+        if self.batch_mode not in ("continuous", "rounds"):
+            raise ValueError("batch_mode must be 'continuous' or 'rounds'")
         self._ctx = _ctx_for(self.maze, 1.0)
         self._tree = _DeviceTree(self._ctx.device)
         self._tree.append(np.asarray(start_state[:2]))
@@ -186,7 +191,7 @@ class RRT_Planner(BasePlanner):
 
     def plan(self):
         if self.batch_size > 1:
-            return self._plan_batched()
+            return self._plan_continuous() if self.batch_mode == "continuous" else self._plan_batched()
         start_time = time.time()
         curr_time = time.time()
         total_diffusion_time = 0
@@ -266,7 +271,151 @@ class RRT_Planner(BasePlanner):
         self.env.prob_map = orig_prob_map
         return self.handle_goal_reached(best, iter_num, start_time)
 
-    # ---- batched expansion --------------------------------------------------------------------
+    # ---- batched expansion, continuous refill ---------------------------------------------------
+    def _plan_continuous(self):
+        """B slots, each running one iteration chain of the reference's loop (sample -> nearest node -> an edge
+        of up to edge_length / action_horizon chunks, RRT.py:130-211).  Every device pass advances all B
+        slots by one chunk (local map -> conditioning -> sampler -> propagate + collide); a slot whose edge
+        ended -- collision: edge dropped (RRT.py:179-184); goal or full length: node inserted (:201-207) --
+        is refilled at once, so no slot idles while others finish.  Two slot groups alternate on the stream:
+        while one group's pass runs on the GPU the host books the other group's results, draws its
+        replacement samples and finds their nearest nodes.  One packed host->device and one packed
+        device->host copy per pass (pinned buffers)."""
+        start_time = time.time()
+        B = self.batch_size
+        smp = self.sampler
+        n_map = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
+        ctx = smp._context()
+        self._ctx = _ctx_for(self.maze, self.s_global)
+        dev = ctx.device
+        h = self.action_horizon
+        A = smp.action_dim
+        mean_np = smp.metadata["Actions_mean"].astype(np.float32)
+        goal_xy = np.asarray(self.env.goal, dtype=np.float64)
+        sched = self.prop_duration_schedule
+        iter_num = 0
+        has_obstacle_ahead = []
+        orig_prob_map = self.env.prob_map.copy()
+        if self.run_type >= 3:
+            self.env.update_prob_map_by_loc()
+        W_IN = 6 + A + 2                      # state | previous action | conditioning goal
+        W_OUT = h * 6 + h * A + 6 + 2         # trajectory | actions | final state | first_coll, done_step
+
+        class Group:
+            pass
+        groups = []
+        for _ in range(2):
+            g = Group()
+            g.h_in = torch.empty((B, W_IN), dtype=torch.float32).pin_memory()
+            g.h_out = torch.empty((B, W_OUT), dtype=torch.float32).pin_memory()
+            g.parent = [None] * B              # Node the slot's edge grows from
+            g.chunk = np.zeros(B, dtype=np.int64)
+            g.n_chunks = np.ones(B, dtype=np.int64)
+            g.a_seq = [[] for _ in range(B)]
+            g.s_seq = [[] for _ in range(B)]
+            g.event = torch.cuda.Event()
+            g.in_flight = False
+            groups.append(g)
+
+        def refill(g, slots):
+            k = len(slots)
+            if k == 0:
+                return
+            samples, goals = self._sample_batch(k)
+            parents = self.nearest_node_batch(samples)
+            hin = g.h_in.numpy()
+            for j, b in enumerate(slots):
+                p = parents[j]
+                g.parent[b] = p
+                g.n_chunks[b] = max(1, sched[min(max(p.num_visit, 0), len(sched) - 1)] // h)
+                p.num_visit += 1
+                g.chunk[b] = 0
+                g.a_seq[b] = []
+                g.s_seq[b] = []
+                hin[b, :6] = p.state
+                hin[b, 6:6 + A] = mean_np if p.parent_action_seq is None or len(p.parent_action_seq) == 0 \
+                    else p.parent_action_seq[-1]
+            hin[slots, 6 + A:] = goals
+
+        def launch(g):
+            d_in = g.h_in.to(dev, non_blocking=True)
+            states, prev, goals_d = d_in[:, :6].contiguous(), d_in[:, 6:6 + A].contiguous(), d_in[:, 6 + A:].contiguous()
+            lm = ctx.local_map(states, n_map, self.local_map_scale, bf16_signed=True)
+            cond = ctx.build_cond_car(states, prev, goals_d, smp.metadata, float(n_map))
+            noise = torch.randn((B, smp.pred_horizon, A), device=dev)
+            a = ctx.fm_sample(noise, cond, lm, smp.num_diffusion_iters, smp.metadata["Actions_mean"], smp.metadata["Actions_std"])
+            res = ctx.propagate_collide(states, a, goal_xy, S=h, want_traj=True)
+            packed = torch.cat([res["traj"].reshape(B, h * 6), a[:, :h].reshape(B, h * A), res["final"],
+                                res["first_coll"].float()[:, None], res["done_step"].float()[:, None]], 1)
+            g.h_out.copy_(packed, non_blocking=True)
+            g.event.record()
+            g.in_flight = True
+
+        def harvest(g):
+            """Book one finished pass of group g; returns the goal node if some slot reached the goal."""
+            g.event.synchronize()
+            g.in_flight = False
+            out = g.h_out.numpy().astype(np.float64)
+            hin = g.h_in.numpy()
+            traj = out[:, :h * 6].reshape(B, h, 6)
+            acts = out[:, h * 6:h * 6 + h * A].reshape(B, h, A)
+            fin = out[:, h * 6 + h * A:h * 6 + h * A + 6]
+            first = out[:, -2].astype(np.int64)
+            done = out[:, -1].astype(np.int64)
+            new_nodes, goal_node = [], None
+            coll = first >= 0                      # collision: the whole edge is dropped (RRT.py:179-184)
+            steps = np.where(done >= 0, done + 1, h)
+            s0 = hin[:, :6].astype(np.float64)
+            g.chunk[~coll] += 1
+            ends = ~coll & ((done >= 0) | (g.chunk >= g.n_chunks))
+            goes_on = ~coll & ~ends
+            a_seq, s_seq = g.a_seq, g.s_seq
+            for b in np.nonzero(~coll)[0]:
+                n = steps[b]
+                a_seq[b].append(acts[b, :n])
+                s_seq[b].append(s0[b:b + 1])       # every chunk starts with its start state,
+                s_seq[b].append(traj[b, :n])       # like the reference's states_sequence
+            for b in np.nonzero(ends)[0]:
+                node = Node(fin[b].copy(), np.concatenate(a_seq[b]), np.concatenate(s_seq[b])[None], parent=g.parent[b])
+                new_nodes.append(node)
+                if done[b] >= 0 and goal_node is None:
+                    goal_node = node
+            hin[goes_on, :6] = fin[goes_on]        # the edge goes on from the state it reached
+            hin[goes_on, 6:6 + A] = acts[goes_on, h - 1]
+            free = np.nonzero(coll | ends)[0].tolist()
+            self._insert_many(new_nodes)
+            if self.run_type == 0:
+                has_obstacle_ahead.extend([False] * len(new_nodes))
+            else:
+                has_obstacle_ahead.extend(self.check_obstacle_ahead(nd.state) for nd in new_nodes)
+            return goal_node, free
+
+        for g in groups:
+            refill(g, list(range(B)))
+        turn = 0
+        while (time.time() - start_time) < self.time_budget:
+            if self.iteration_cap is not None and iter_num >= self.iteration_cap:
+                break
+            g = groups[turn]
+            turn ^= 1
+            if g.in_flight:
+                goal_node, free = harvest(g)
+                if goal_node is not None:
+                    torch.cuda.current_stream(dev).synchronize()
+                    self.env.prob_map = orig_prob_map
+                    return self.handle_goal_reached(goal_node, iter_num, start_time)
+                refill(g, free)
+            launch(g)
+            iter_num += B
+        for g in groups:                          # book what is still in flight
+            if g.in_flight:
+                goal_node, _ = harvest(g)
+                if goal_node is not None:
+                    self.env.prob_map = orig_prob_map
+                    return self.handle_goal_reached(goal_node, iter_num, start_time)
+        return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)
+
+    # ---- batched expansion, one round of edges at a time ------------------------------------------
     def _plan_batched(self):
         from ..expansion import TreeExpander
         start_time = time.time()

@@ -217,7 +217,8 @@ def test_tree_sampler_calls_match_reference(car_meta):
     assert rel(out[:, :8], g["call_actions"]) < 2e-2
 
 
-def test_batched_planner_runs(mazes, car_meta):
+@pytest.mark.parametrize("mode", ["continuous", "rounds"])
+def test_batched_planner_runs(mazes, car_meta, mode):
     """batch_size > 1: a tree grown by batched device passes; structural invariants of every edge."""
     from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler
     sd = dref.init_params(seed=21, input_dim=2, cond_dim=7, emb_dim=400, down_dims=[64, 128, 256])
@@ -228,10 +229,12 @@ def test_batched_planner_runs(mazes, car_meta):
     torch.manual_seed(0)
     np.random.seed(0)
     random.seed(0)
-    pl = make_planner(grid, g["start"], g["goal"], sampler=smp, time_budget=30, batch_size=128, iteration_cap=128 * 8 * 6)
+    pl = make_planner(grid, g["start"], g["goal"], sampler=smp, time_budget=30, batch_size=128, iteration_cap=128 * 8 * 6,
+                      batch_mode=mode)
     pl.reset()
     path, actions = pl.plan()
     assert len(pl.node_list) > 10
+    assert pl.results["iterations"] >= 128 and all(nd.parent in pl.node_list for nd in pl.node_list[1:])
     for nd in pl.node_list[1:]:
         a, s = nd.parent_action_seq, nd.parent_states_seq[0]
         assert 1 <= len(a) <= 64 and len(s) == len(a) + int(np.ceil(len(a) / 8))

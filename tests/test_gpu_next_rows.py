@@ -99,3 +99,55 @@ def test_mppi_controller_tracks_reference_path(mazes):
             break
     assert np.linalg.norm(state[:2] - goal[:2]) < d0 - 1.0  # moved along the corridor toward the goal
     assert abs(state[1] + 7.5) < 0.6                          # and stayed on the reference line
+
+
+class _SteerToGoal:
+    """Scripted stand-in for the policy: constant gentle throttle, steering proportional to the bearing of the
+    conditioning goal (enough to drive a corridor and to swerve when a replan samples a new sub-goal)."""
+
+    def __call__(self, obs_seq, prev_actions=None, goal=None, local_map=None):
+        s = np.asarray(obs_seq, dtype=np.float64).reshape(-1, 6)[-1]
+        g = np.asarray(goal, dtype=np.float64).reshape(-1)[:2]
+        bearing = np.arctan2(g[1] - s[1], g[0] - s[0]) - s[2]
+        bearing = (bearing + np.pi) % (2 * np.pi) - np.pi
+        a = np.zeros((1, 64, 2))
+        a[0, :, 0] = 1.5 if s[3] < 1.0 else -0.5          # keep the speed near 1 m/s
+        a[0, :, 1] = np.clip(2.0 * (np.clip(bearing, -0.35, 0.35) - s[5]), -2, 2)
+        return a
+
+
+def test_online_episode_replans_around_a_discovered_obstacle(mazes):
+    """run_scenarios_with_lidar_DiTree main loop on the device kernels: plan on the known map, drive, scan every
+    0.2 s, find the inserted obstacle on the main path, replan, finish (goal, or a bounded number of actions)."""
+    import random
+    from ditreeonlineplanner_b200.car_env import CarEnv
+    from ditreeonlineplanner_b200.online import run_online_episode
+    from ditreeonlineplanner_b200.planners.RRT import RRT_Planner
+    base = np.zeros((20, 20))
+    base[0, :] = base[-1, :] = base[:, 0] = base[:, -1] = 1          # an empty room ...
+    base[9:12, 6] = 1                                                # ... with a known pillar in front of the start
+    true_map = base.copy()
+    true_map[7:14, 11] = 1                                           # an unknown wall in the pillar's lidar shadow
+    env = CarEnv(maze_map=base.copy(), collision_checking=False, run_type=0)
+    start = np.array([*env.cell_rowcol_to_xy(np.array([10, 3])), 0.0, 0, 0, 0])
+    goal = np.array([*env.cell_rowcol_to_xy(np.array([10, 16])), 0, 0, 0, 0])
+    pl = RRT_Planner(start, goal, env_id="carmaze", environment=env, sampler=_SteerToGoal(), action_horizon=8,
+                     local_map_size=20, local_map_scale=0.2, global_map_scale=1.0, goal_conditioning_bias=0.85,
+                     prop_duration=[64], time_budget=20, iteration_cap=4000, run_type=0)
+    random.seed(3)
+    np.random.seed(3)
+    out = run_online_episode(pl, start, goal, base, true_map, run_type=0, offline_time_budget=20, max_actions=3000)
+    path, acts = out["executed_path"], out["executed_actions"]
+    assert out["scans"] >= 2 and len(path) == len(acts) and len(path) > 20
+    # the lidar found (part of) the inserted wall and the planner's map holds it
+    assert out["known_maze"][7:14, 11].sum() >= 1 and np.array_equal(pl.maze, out["known_maze"])
+    assert out["known_maze"][true_map == 0].sum() == 0             # nothing free in truth was marked occupied
+    # the executed trajectory is dynamically consistent: replaying the actions reproduces it
+    ref = orc.rollout_car(start[None], acts[None], goal[:2], out["known_maze"], stop_on_collision=False)
+    np.testing.assert_allclose(path, ref["traj"][0], rtol=2e-3, atol=2e-3)
+    # it never drove through a wall of the true map, and it replanned once the wall was seen on its path
+    assert not orc.collide_car_batch(path[:, :3], true_map).any() or out["success"] is None
+    assert out["replans"] >= 1
+    if out["success"]:
+        assert np.linalg.norm(path[-1, :2] - goal[:2]) < 0.5
+    assert out["stats"]["iterations"] > 0 and out["stats"]["number_of_nodes"] > 0

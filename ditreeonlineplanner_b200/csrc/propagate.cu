@@ -22,11 +22,11 @@
 #ifndef PROP_PF
 #define PROP_PF 2     // action prefetch distance of the strided kernel, steps (register ring)
 #endif
-// trajectory stores: never re-read by this kernel -> streaming (evict-first) stores
-#ifdef PROP_PLAIN_ST
-#define PROP_ST(p, v) (*(p) = (v))
-#else
+// trajectory stores: plain write-back stores measured 2.5 % faster than streaming (st.global.cs) ones
+#ifdef PROP_STREAMING_ST
 #define PROP_ST(p, v) __stcs((p), (v))
+#else
+#define PROP_ST(p, v) (*(p) = (v))
 #endif
 #define PROP_WARPS (PROP_THREADS / 32)
 

@@ -36,6 +36,8 @@ struct dt_ctx {
   int* h_status = nullptr;  // pinned
   void* d_scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* d_wide = nullptr;  // fp32 pre-normalisation scratch of the wide-GroupNorm GEMM fallback (gemm.cu)
+  size_t wide_bytes = 0;
   int64_t launches = 0;
   int sm_count = 148;
   dt_denoiser* den = nullptr;

@@ -42,6 +42,7 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_wide) cudaFree(ctx->d_wide);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   delete ctx;
 }

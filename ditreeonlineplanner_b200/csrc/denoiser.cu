@@ -554,9 +554,11 @@ extern "C" int dt_load_denoiser(dt_ctx* ctx, const dt_tensor_desc* tensors, int 
     return dt_fail(ctx, DT_E_UNSUPPORTED, "pred_horizon must be a power of two in 4..128");
   for (int l = 0; l < 3; ++l) {
     const int gw = C[l] / 8;
-    if (C[l] % 64 != 0 || (gw != 8 && gw != 16 && gw != 32 && gw != 64 && gw != 128 && gw != 256))
+    // group widths up to 256 are normalised inside the GEMM epilogue; wider ones (xlarge's 512) take the
+    // plain-epilogue GEMM + k_gn_mish_wide fallback (gemm.cu)
+    if (C[l] % 64 != 0 || (gw != 8 && gw != 16 && gw != 32 && gw != 64 && gw != 128 && gw != 256 && gw != 512 && gw != 1024))
       return dt_fail(ctx, DT_E_UNSUPPORTED,
-                     "down_dims must be multiples of 64 with GroupNorm group width (C/8) in {8,...,256}");
+                     "down_dims must be multiples of 64 with GroupNorm group width (C/8) in {8,...,1024}");
   }
   if (cfg->max_batch < 1) return dt_fail(ctx, DT_E_ARG, "max_batch must be positive");
   TMap tm;

@@ -844,10 +844,114 @@ static int gemm_cta_group() {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GroupNorm groups wider than one N tile (the `xlarge` preset: 4096 / 8 = 512 channels): the statistics of
+// a group cannot be taken inside one CTA's accumulator, so the GEMM runs with the plain epilogue into an
+// fp32 scratch and this kernel applies GroupNorm -> Mish -> FiLM (+ residual) per (sample, group).
+// One block per (sample, group): T x GW fp32 values, two passes over them (they stay in L2 / L1).
+// ---------------------------------------------------------------------------------------------
+struct WideGn {
+  const float* y;        // [B*T][N] fp32, bias already added
+  int T, N, gw;
+  const float* gamma;
+  const float* beta;
+  const float* film;     // [B][film_ld] or null
+  long long film_ld;
+  const float* film_t;   // [2N] or null
+  const __nv_bfloat16* resid;
+  long long ld_res;
+  __nv_bfloat16* out;
+  long long ldc, out_b_stride, out_t_stride, out_off;
+};
+
+__global__ void __launch_bounds__(256)
+k_gn_mish_wide(WideGn p) {
+  __shared__ float s_a[256], s_b[256];
+  const int groups = p.N / p.gw;
+  const long long b = blockIdx.x / groups;
+  const int grp = blockIdx.x % groups;
+  const int n0 = grp * p.gw;
+  const int cnt = p.T * p.gw;
+  const float* base = p.y + b * p.T * (long long)p.N + n0;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += 256) {
+    const int t = i / p.gw, c = i - t * p.gw;
+    const float v = base[(long long)t * p.N + c];
+    s += v;
+    ss += v * v;
+  }
+  s_a[threadIdx.x] = s;
+  s_b[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float mean = s_a[0] / (float)cnt;
+  const float var = fmaxf(s_b[0] / (float)cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  for (int i = threadIdx.x; i < cnt; i += 256) {
+    const int t = i / p.gw, c = i - t * p.gw, n = n0 + c;
+    float v = mish_f((base[(long long)t * p.N + c] - mean) * rstd * p.gamma[n] + p.beta[n]);
+    if (p.film) {
+      const float sc = p.film[b * p.film_ld + n] + (p.film_t ? p.film_t[n] : 0.f);
+      const float sh = p.film[b * p.film_ld + p.N + n] + (p.film_t ? p.film_t[p.N + n] : 0.f);
+      v = v * sc + sh;
+    }
+    const long long row = b * p.out_b_stride + (long long)t * p.out_t_stride + p.out_off;
+    if (p.resid) v += __bfloat162float(p.resid[row * p.ld_res + n]);
+    p.out[row * p.ldc + n] = __float2bfloat16(v);
+  }
+}
+
+int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);
+
+static int conv_gemm_wide_gn(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
+  if (g.N % g.group_width != 0 || !g.gamma || !g.beta || !g.out_bf16)
+    return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad wide GroupNorm problem");
+  const size_t need = (size_t)g.B * g.T * g.N * sizeof(float);
+  if (need > ctx->wide_bytes) {
+    DT_CUDA(cudaStreamSynchronize(st));
+    if (ctx->d_wide) DT_CUDA(cudaFree(ctx->d_wide));
+    ctx->d_wide = nullptr;
+    ctx->wide_bytes = 0;
+    DT_CUDA(cudaMalloc(&ctx->d_wide, need));
+    ctx->wide_bytes = need;
+  }
+  ConvGemm plain = g;
+  plain.epi = EPI_PLAIN;
+  plain.gamma = plain.beta = nullptr;
+  plain.film = plain.film_t = nullptr;
+  plain.resid = nullptr;
+  plain.relu = 0;
+  plain.out_bf16 = nullptr;
+  plain.out_f32 = (float*)ctx->d_wide;
+  plain.ldc = g.N;
+  plain.out_b_stride = g.T;
+  plain.out_t_stride = 1;
+  plain.out_off = 0;
+  int rc = dt_conv_gemm(ctx, plain, st);
+  if (rc) return rc;
+  WideGn p;
+  p.y = (const float*)ctx->d_wide; p.T = g.T; p.N = g.N; p.gw = g.group_width;
+  p.gamma = g.gamma; p.beta = g.beta; p.film = g.film; p.film_ld = g.film_ld; p.film_t = g.film_t;
+  p.resid = g.resid; p.ld_res = g.ld_res; p.out = g.out_bf16; p.ldc = g.ldc;
+  p.out_b_stride = g.out_b_stride; p.out_t_stride = g.out_t_stride; p.out_off = g.out_off;
+  const long long blocks = g.B * (g.N / g.group_width);
+  if (blocks > 0x7fffffffLL) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_conv_gemm: batch too large for the wide GroupNorm path");
+  k_gn_mish_wide<<<(unsigned)blocks, 256, 0, st>>>(p);
+  DT_LAUNCH_CHECK("k_gn_mish_wide");
+  return DT_OK;
+}
+
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (g.B <= 0) return DT_OK;
   if (g.nseg < 1 || g.nseg > GEMM_MAX_SEG || !g.w || !g.a[0].ptr || g.N % 64 != 0)
     return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad problem description");
+  if (g.epi == EPI_GN_MISH && g.group_width > 256) return conv_gemm_wide_gn(ctx, g, st);
   // tile geometry: a tile holds whole samples (T <= 128) or a 128-row slice of one sample
   int T = g.T, rows_t, nb, tps;
   if (T >= BM) {

@@ -151,3 +151,34 @@ def test_online_episode_replans_around_a_discovered_obstacle(mazes):
     if out["success"]:
         assert np.linalg.norm(path[-1, :2] - goal[:2]) < 0.5
     assert out["stats"]["iterations"] > 0 and out["stats"]["number_of_nodes"] > 0
+
+
+def test_mpc_planner_mirror(mazes, car_meta=None):
+    """planners/MPC.py: receding-horizon chains from the start; scalar loop with a scripted sampler reaches the
+    goal across an empty room, and the batched flavour returns a dynamically consistent winning chain."""
+    from ditreeonlineplanner_b200.car_env import CarEnv
+    from ditreeonlineplanner_b200.planners.MPC import MPC_Planner
+    from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler
+    room = np.zeros((20, 20))
+    room[0, :] = room[-1, :] = room[:, 0] = room[:, -1] = 1
+    env = CarEnv(maze_map=room.copy(), collision_checking=False)
+    start = np.array([*env.cell_rowcol_to_xy(np.array([10, 3])), 0.0, 0, 0, 0])
+    goal = np.array([*env.cell_rowcol_to_xy(np.array([10, 9])), 0, 0, 0, 0])
+    pl = MPC_Planner(start, goal, env, _SteerToGoal(), env_id="carmaze", action_horizon=8, local_map_size=20,
+                     local_map_scale=0.2, global_map_scale=1.0, time_budget=20)
+    pl.reset()
+    path, actions = pl.plan()
+    assert path is not None and np.linalg.norm(path[-1, :2] - goal[:2]) < 0.5
+    ref = orc.rollout_car(start[None], actions[None].astype(np.float64), goal[:2], room, stop_on_collision=False)
+    assert ref["done_step"][0] >= 0
+    # batched chains with a random-init small denoiser: bookkeeping only (a random policy rarely arrives)
+    sd = dref.init_params(seed=21, input_dim=2, cond_dim=7, emb_dim=400, down_dims=[64, 128, 256])
+    smp = DiffusionSampler(sd, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2, obs_history=1,
+                           action_history=1, goal_conditioned=True, num_diffusion_iters=1, local_map_size=20, max_batch=64)
+    plb = MPC_Planner(start, goal, env, smp, env_id="carmaze", action_horizon=8, local_map_size=20, local_map_scale=0.2,
+                      global_map_scale=1.0, time_budget=20, batch_size=64, iteration_cap=64 * 12)
+    plb.reset()
+    pathb, actb = plb.plan()
+    assert plb.results["iterations"] >= 64
+    if pathb is not None:
+        assert np.linalg.norm(pathb[-1, :2] - goal[:2]) < 0.5 and actb.shape[1] == 2

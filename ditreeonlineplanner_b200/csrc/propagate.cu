@@ -277,12 +277,7 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
     const int nb = (int)((Bn - t0 < 32u) ? (Bn - t0) : 32u);
     const int cs = (a.S - ch * PROP_CH < PROP_CH) ? (a.S - ch * PROP_CH) : PROP_CH;
     const uint32_t dst = s_act_u + (uint32_t)buf * (32 * PROP_APITCH * 4);
-#ifdef PROP_EXP_NOLOAD  // experiment: no action loads (staging rows stay zero)
-    if (cs >= 0) {
-    } else if (cs == PROP_CH) {
-#else
     if (cs == PROP_CH) {
-#endif
       // 32 candidates x 2 float4: lane -> candidates c8 + 8 * (q4 >> 1) (+16), column q4 & 1
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -304,10 +299,6 @@ k_propagate_rows(MapView m, QMapView q, PropArgs a, int* __restrict__ status) {
   };
 
   uint32_t t0 = (blockIdx.x * PROP_RWARPS + warp) * 32u;
-#ifdef PROP_EXP_NOLOAD
-  for (int k = lane; k < 2 * 32 * PROP_APITCH; k += 32) s_act[k] = 0.f;
-  __syncwarp();
-#endif
   if (t0 < Bn && a.S > 0) issue(t0, 0, 0);
   int buf = 0;
   Car c = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};

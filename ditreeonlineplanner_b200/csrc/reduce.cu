@@ -44,6 +44,54 @@ k_nearest(const float* __restrict__ nx, const float* __restrict__ ny, int64_t n,
   }
 }
 
+// k nearest nodes per query (KDTree.query(x, k) of planners/RRT.py:50 for k > 1): one warp per query; every
+// lane keeps the DT_KNN_MAX best (d^2, index) pairs of its stripe sorted in registers, then the warp extracts
+// the global k smallest with k rounds of shuffle arg-min (the winning lane pops its head).  Ascending
+// distance, lowest index first on ties; slots beyond n get index n (SciPy's "missing neighbour" marker).
+#define DT_KNN_MAX 16
+
+template <int KMAX>
+__global__ void __launch_bounds__(RED_THREADS)
+k_nearest_k(const float* __restrict__ nx, const float* __restrict__ ny, int64_t n, const float* __restrict__ qx,
+            const float* __restrict__ qy, int64_t q_stride, int64_t Q, int k, int32_t* __restrict__ out) {
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t q = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); q < Q; q += (int64_t)gridDim.x * wpb) {
+    const double x = (double)qx[q * q_stride], y = (double)qy[q * q_stride];
+    double bd[KMAX];
+    int bi[KMAX];
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) { bd[s] = INF; bi[s] = 0x7fffffff; }
+    for (int64_t j = lane; j < n; j += 32) {
+      const double dx = xsub(x, (double)nx[j]), dy = xsub(y, (double)ny[j]);
+      double d = xadd(xmul(dx, dx), xmul(dy, dy));
+      int id = (int)j;
+      if (d < bd[KMAX - 1]) {   // insertion into the sorted list (indices ascend within a stripe: strict <)
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) {
+          if (d < bd[s]) {
+            const double td = bd[s]; const int ti = bi[s];
+            bd[s] = d; bi[s] = id;
+            d = td; id = ti;
+          }
+        }
+      }
+    }
+    for (int r = 0; r < k; ++r) {
+      double d = bd[0];
+      int id = bi[0];
+      warp_argmin(d, id);
+      if (bi[0] == id && id != 0x7fffffff) {  // the owner pops its head
+#pragma unroll
+        for (int s = 0; s + 1 < KMAX; ++s) { bd[s] = bd[s + 1]; bi[s] = bi[s + 1]; }
+        bd[KMAX - 1] = INF; bi[KMAX - 1] = 0x7fffffff;
+      }
+      if (lane == 0) out[q * k + r] = (id == 0x7fffffff) ? (int32_t)n : id;
+    }
+  }
+}
+
 // Block-wide arg-min of a per-node cost.  planners/RRT.py:233-237.
 __global__ void __launch_bounds__(1024)
 k_goal_cost_argmin(const float* __restrict__ nx, const float* __restrict__ ny, int64_t n, double gx, double gy,
@@ -201,6 +249,23 @@ extern "C" int dt_nearest(dt_ctx* ctx, const float* node_x, const float* node_y,
   if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
   k_nearest<<<(int)blocks, RED_THREADS, 0, (cudaStream_t)stream>>>(node_x, node_y, n, qx, qy, q_stride, Q, idx_out);
   DT_LAUNCH_CHECK("k_nearest");
+  return DT_OK;
+}
+
+extern "C" int dt_nearest_k(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, const float* qx,
+                            const float* qy, int64_t q_stride, int64_t Q, int k, int32_t* idx_out, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (Q <= 0) return DT_OK;
+  if (n <= 0 || !node_x || !node_y || !qx || !qy || !idx_out || k < 1)
+    return dt_fail(ctx, DT_E_ARG, "dt_nearest_k: bad argument");
+  if (k > DT_KNN_MAX) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_nearest_k: k <= 16");
+  const int wpb = RED_THREADS / 32;
+  int64_t blocks = (Q + wpb - 1) / wpb;
+  if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k <= 4) k_nearest_k<4><<<(int)blocks, RED_THREADS, 0, st>>>(node_x, node_y, n, qx, qy, q_stride, Q, k, idx_out);
+  else k_nearest_k<DT_KNN_MAX><<<(int)blocks, RED_THREADS, 0, st>>>(node_x, node_y, n, qx, qy, q_stride, Q, k, idx_out);
+  DT_LAUNCH_CHECK("k_nearest_k");
   return DT_OK;
 }
 

@@ -245,6 +245,16 @@ class Context:
                                         q.stride(0), q.shape[0], _ptr(out), self._stream()))
         return out
 
+    def nearest_k(self, node_x, node_y, queries, k):
+        """KDTree.query(queries, k) indices: (Q, k) int32, ascending distance, n = missing neighbour."""
+        nx, ny = self._f32(node_x).contiguous(), self._f32(node_y).contiguous()
+        q = self._f32(queries)
+        assert q.dim() == 2 and q.stride(1) == 1
+        out = torch.empty((q.shape[0], int(k)), dtype=torch.int32, device=self.device)
+        self._check(self.lib.dt_nearest_k(self.h, _ptr(nx), _ptr(ny), nx.shape[0], _ptr(q[:, 0]), _ptr(q[:, 1]),
+                                          q.stride(0), q.shape[0], int(k), _ptr(out), self._stream()))
+        return out
+
     def goal_cost_argmin(self, node_x, node_y, goal_xy, ahead=None):
         nx, ny = self._f32(node_x).contiguous(), self._f32(node_y).contiguous()
         if ahead is not None:

@@ -128,6 +128,12 @@ int dt_build_cond_ant(dt_ctx* ctx, const float* obs_seq, int h, int obs_history,
 int dt_nearest(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, const float* qx, const float* qy,
                int64_t q_stride, int64_t Q, int32_t* idx_out, void* stream);
 
+/* k nearest nodes per query: kd_tree.query(sample, k) (planners/RRT.py:50 uses k = 1; SciPy's API for k > 1):
+ * idx_out (Q, k) i32, ascending squared distance (float64), lowest index first on ties, n marks a missing
+ * neighbour when k > n.  1 <= k <= 16. */
+int dt_nearest_k(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, const float* qx, const float* qy,
+                 int64_t q_stride, int64_t Q, int k, int32_t* idx_out, void* stream);
+
 /* Final node selection (planners/RRT.py:233-237): argmin_i ||p_i - goal|| + 1e4*ahead[i] (ahead
  * nullable), float64, first index on ties; idx_out[0]. */
 int dt_goal_cost_argmin(dt_ctx* ctx, const float* node_x, const float* node_y, int64_t n, float goal_x, float goal_y,

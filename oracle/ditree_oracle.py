@@ -408,6 +408,20 @@ def nearest(node_xy, query_xy):
     return out
 
 
+def nearest_k(node_xy, query_xy, k):
+    """KDTree.query(query, k) indices (planners/RRT.py:50 with k > 1): ascending float64 squared distance,
+    lowest index first on ties, n marks a missing neighbour (SciPy's convention) when k > n."""
+    node_xy = np.asarray(node_xy, dtype=np.float64)
+    query_xy = np.asarray(query_xy, dtype=np.float64)
+    n = len(node_xy)
+    out = np.full((len(query_xy), k), n, dtype=np.int64)
+    for i, q in enumerate(query_xy):
+        d2 = (q[0] - node_xy[:, 0]) ** 2 + (q[1] - node_xy[:, 1]) ** 2
+        order = np.argsort(d2, kind="stable")[:k]
+        out[i, :len(order)] = order
+    return out
+
+
 def final_node_cost_argmin(node_xy, goal_xy, obstacle_ahead):
     """planners/RRT.py:233-237: argmin over nodes of dist-to-goal + 10e3 * obstacle_ahead."""
     d = np.linalg.norm(np.asarray(node_xy, dtype=np.float64) - np.asarray(goal_xy, dtype=np.float64), axis=1)

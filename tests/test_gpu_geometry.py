@@ -251,6 +251,32 @@ def test_nearest(ctx, n):
     assert (got == idx).mean() > 0.999
 
 
+@pytest.mark.parametrize("n,k", [(1, 1), (3, 5), (100, 4), (5000, 8), (100_000, 16)])
+def test_nearest_k_vs_oracle_and_kdtree(ctx, n, k):
+    from scipy.spatial import KDTree
+    rng = np.random.default_rng(n + k)
+    nodes = rng.uniform(-10, 10, (n, 2)).astype(np.float32)
+    if n > 50:
+        nodes[7] = nodes[3]                       # exact duplicates: lowest index first
+        nodes[11] = nodes[3]
+    q = np.concatenate([rng.uniform(-10, 10, (300, 2)).astype(np.float32), nodes[:min(n, 20)]])
+    got = ctx.nearest_k(dev(nodes[:, 0]), dev(nodes[:, 1]), dev(q), k).cpu().numpy()
+    want = orc.nearest_k(nodes, q, k)
+    bad = np.nonzero(np.any(got != want, axis=1))[0]
+    assert len(bad) == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
+    # SciPy's KD-tree agrees wherever the neighbour distances are distinct (its tie order is unspecified)
+    kk = min(k, n)
+    k1 = min(k + 1, n)                             # one more neighbour: a tie at the cut-off is a tie too
+    d, idx = KDTree(nodes.astype(np.float64)).query(q.astype(np.float64), k=k1)
+    d, idx = d.reshape(len(q), k1), idx.reshape(len(q), k1)
+    distinct = np.ones(len(q), bool) if k1 == 1 else np.all(np.diff(d, axis=1) > 0, axis=1)
+    assert distinct.mean() > 0.5
+    assert np.array_equal(got[distinct][:, :kk], idx[distinct][:, :kk])
+    # k = 1 is dt_nearest
+    one = ctx.nearest(dev(nodes[:, 0]), dev(nodes[:, 1]), dev(q)).cpu().numpy()
+    assert np.array_equal(one, got[:, 0])
+
+
 def test_nearest_ties_and_argmin(ctx):
     nodes = np.array([[0, 0], [1, 0], [0, 0], [1, 0]], np.float32)
     got = ctx.nearest(dev(nodes[:, 0]), dev(nodes[:, 1]), dev([[0.1, 0], [0.9, 0], [0.5, 0]])).cpu().tolist()

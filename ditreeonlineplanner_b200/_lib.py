@@ -40,6 +40,7 @@ SIGNATURES = {
     "dt_edt_prior": (C.c_int, [c_p, c_p, c_p]),
     "dt_prob_map": (C.c_int, [c_p, C.c_int, C.c_int, c_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                               c_p, c_p, c_p]),
+    "dt_log_blend": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_double, C.c_double, c_p, c_p]),
     "dt_sample_cells": (C.c_int, [c_p, c_p, C.c_int, c_p, c_i64, c_p, c_p]),
     "dt_ray_probe": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dt_path_first_obstacle": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),

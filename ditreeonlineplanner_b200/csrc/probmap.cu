@@ -122,6 +122,43 @@ k_prob_map(int H, int W, const double* __restrict__ prior, double rx, double ry,
   }
 }
 
+// combine_log_blend(prior, gauss, beta, obstacle_mask, eps) alone (prob_sampling_utils.py:150-172), for callers
+// that bring their own Gaussian: post = exp(beta log(prior + eps) + (1 - beta) log(gauss + eps)) * (prior > 0),
+// masked, normalised; fallbacks: the (masked) prior, then uniform over the mask.
+__global__ void __launch_bounds__(PM_THREADS)
+k_log_blend(int n, const double* __restrict__ prior, const double* __restrict__ gauss, const uint8_t* __restrict__ mask,
+            double beta, double eps, double* __restrict__ out) {
+  __shared__ double s_red[PM_THREADS];
+  double part = 0.0;
+  for (int c = threadIdx.x; c < n; c += PM_THREADS) {
+    const double pr = prior[c];
+    double post = (pr > 0.0) ? exp(beta * log(pr + eps) + (1.0 - beta) * log(gauss[c] + eps)) : 0.0;
+    if (mask && !mask[c]) post = 0.0;
+    out[c] = post;
+    part += post;
+  }
+  double s = pm_block_sum(part, s_red);
+  if (s <= eps) {
+    part = 0.0;
+    for (int c = threadIdx.x; c < n; c += PM_THREADS) {
+      const double v = (mask && !mask[c]) ? 0.0 : prior[c];
+      out[c] = v;
+      part += v;
+    }
+    s = pm_block_sum(part, s_red);
+    if (s <= eps) {
+      part = 0.0;
+      for (int c = threadIdx.x; c < n; c += PM_THREADS) {
+        const double v = (mask && !mask[c]) ? 0.0 : 1.0;
+        out[c] = v;
+        part += v;
+      }
+      s = pm_block_sum(part, s_red);
+    }
+  }
+  for (int c = threadIdx.x; c < n; c += PM_THREADS) out[c] = out[c] / s;
+}
+
 // cdf = cumsum(p) (sequential, NumPy's order), cdf /= cdf[-1]  -- one thread; n <= 16384
 __global__ void k_cdf(const double* __restrict__ p, int n, double* __restrict__ cdf) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -172,6 +209,15 @@ extern "C" int dt_prob_map(dt_ctx* ctx, int rows, int cols, const double* prior,
   k_prob_map<<<1, PM_THREADS, 0, (cudaStream_t)stream>>>(rows, cols, prior, robot_x, robot_y, goal_x, goal_y, beta,
                                                         1e-12, prob_out, gauss_out);
   DT_LAUNCH_CHECK("k_prob_map");
+  return DT_OK;
+}
+
+extern "C" int dt_log_blend(dt_ctx* ctx, const double* prior, const double* gauss, const uint8_t* obstacle_mask, int n,
+                            double beta, double eps, double* prob_out, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!prior || !gauss || !prob_out || n < 1 || n > DT_MAX_MAP_CELLS) return dt_fail(ctx, DT_E_ARG, "dt_log_blend: bad argument");
+  k_log_blend<<<1, PM_THREADS, 0, (cudaStream_t)stream>>>(n, prior, gauss, obstacle_mask, beta, eps, prob_out);
+  DT_LAUNCH_CHECK("k_log_blend");
   return DT_OK;
 }
 

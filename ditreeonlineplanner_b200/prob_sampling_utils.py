@@ -44,19 +44,11 @@ def gaussian_map(robot, goal, size=(20, 20)):
 
 
 def combine_log_blend(prior, gauss, beta=0.8, obstacle_mask=None, eps=1e-12):
-    """Element-wise on the host arrays handed in (400 cells): the fused device path is `blended_prob_map`."""
+    """Stand-alone blend of caller-supplied arrays (``dt_log_blend``), the reference's fallbacks included."""
     prior = np.asarray(prior, dtype=np.float64)
-    post = np.exp(beta * np.log(prior + eps) + (1.0 - beta) * np.log(np.asarray(gauss) + eps)) * (prior > 0)
-    if obstacle_mask is not None:
-        post = np.where(obstacle_mask, post, 0.0)
-    s = post.sum()
-    if s <= eps:
-        post = prior.copy() if obstacle_mask is None else np.where(obstacle_mask, prior, 0.0)
-        s = post.sum()
-        if s <= eps:
-            post = np.where(obstacle_mask if obstacle_mask is not None else np.ones_like(post, dtype=bool), 1.0, 0.0)
-            s = post.sum()
-    return post / s
+    gauss = np.asarray(gauss, dtype=np.float64)
+    assert prior.shape == gauss.shape
+    return get_context().log_blend(prior, gauss, beta, obstacle_mask, eps).cpu().numpy()
 
 
 def sample_from_pdf(pdf, n_samples=30):

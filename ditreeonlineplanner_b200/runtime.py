@@ -303,6 +303,15 @@ class Context:
         self._check(rc)
         return out, gauss
 
+    def log_blend(self, prior, gauss, beta=0.8, obstacle_mask=None, eps=1e-12):
+        pr, ga = self._f64(prior), self._f64(gauss)
+        assert pr.shape == ga.shape
+        mask = None if obstacle_mask is None else torch.as_tensor(np.asarray(obstacle_mask, dtype=bool)).to(self.device, torch.uint8).contiguous()
+        out = torch.empty_like(pr)
+        self._check(self.lib.dt_log_blend(self.h, _ptr(pr), _ptr(ga), _ptr(mask), pr.numel(), float(beta), float(eps),
+                                          _ptr(out), self._stream()))
+        return out
+
     def sample_cells(self, prob, u):
         """np.random.choice(prob.size, p=prob.ravel()) for the uniform draws u (B,) -> (B,) int32 flat indices."""
         p = self._f64(prob).reshape(-1)

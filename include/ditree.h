@@ -160,6 +160,11 @@ int dt_edt_prior(dt_ctx* ctx, double* prior_out, void* stream);
 int dt_prob_map(dt_ctx* ctx, int rows, int cols, const double* prior, double robot_x, double robot_y, double goal_x,
                 double goal_y, double beta, double* prob_out, double* gauss_out, void* stream);
 
+/* combine_log_blend(prior, gauss, beta, obstacle_mask, eps) alone (prob_sampling_utils.py:150-172); obstacle_mask:
+ * n bytes (non-zero = free) or NULL.  prior, gauss, prob_out: n float64, device. */
+int dt_log_blend(dt_ctx* ctx, const double* prior, const double* gauss, const uint8_t* obstacle_mask, int n, double beta,
+                 double eps, double* prob_out, void* stream);
+
 /* BasePlanner.sample_row_col_from_probability_map (planners/base_planner.py:157-160) for B draws:
  * np.random.choice(n, p = prob) is cdf = cumsum(prob); cdf /= cdf[-1]; searchsorted(cdf, u, side='right') with
  * u ~ U[0,1) from the caller's generator; idx_out[b] is the flat cell index (bit-exact vs NumPy for the same u).

@@ -32,6 +32,38 @@ out = {}
 ctx = get_context(0)
 rng = np.random.default_rng(0)
 
+# ---------------- C1: the reference's own loop, B = 1 (configs[0]) ----------------
+import random  # noqa: E402
+import time  # noqa: E402
+from ditreeonlineplanner_b200 import load_scenarios  # noqa: E402
+from ditreeonlineplanner_b200 import scenarios as sc  # noqa: E402
+from ditreeonlineplanner_b200.car_env import CarEnv  # noqa: E402
+from ditreeonlineplanner_b200.planners.RRT import RRT_Planner  # noqa: E402
+from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler  # noqa: E402
+row = load_scenarios("test_scenarios_car")[0]
+maze = load_maze(row["maze_name"])
+env = CarEnv(maze_map=maze, collision_checking=False)
+start, goal_s = sc.scenario_states(row, env)
+smp = DiffusionSampler(random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=UNET_DIMS["large"]), None,
+                       "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2, obs_history=1, action_history=1,
+                       goal_conditioned=True, num_diffusion_iters=1, local_map_size=20, max_batch=64).eval()
+pl = RRT_Planner(start, goal_s, env_id="carmaze", environment=env, sampler=smp, prediction_type="actions",
+                 action_horizon=8, local_map_size=20, local_map_scale=0.2, global_map_scale=1.0,
+                 goal_conditioning_bias=0.85, prop_duration=[64], time_budget=1e9, max_iter=300, iteration_cap=100)
+for cap in (40, 1000):   # warm-up, then timed
+    pl.iteration_cap = cap
+    torch.manual_seed(42); np.random.seed(42); random.seed(42)
+    pl.reset()
+    t0 = time.time()
+    pl.plan()
+    torch.cuda.synchronize()
+    dt_c1 = time.time() - t0
+out["C1_reference_loop_B1"] = {"scenario": row["scenario_name"], "iterations": pl.results["iterations"], "seconds": dt_c1,
+                               "iterations_per_s": pl.results["iterations"] / dt_c1, "nodes": len(pl.node_list),
+                               "note": "RRT_Planner.plan() exactly as the reference drives it (one candidate per iteration, "
+                                       "K = 1 = cfgs/carmaze.yaml planning_diffusion_iters, large denoiser): latency-bound, ~110 kernel "
+                                       "launches per iteration; batch_size > 1 is the throughput path"}
+
 # ---------------- C4: lidar + MPPI ----------------
 boxes = load_maze("boxes").astype(np.float32)
 ctx.set_map(boxes)

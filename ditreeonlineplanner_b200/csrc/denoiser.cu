@@ -23,6 +23,7 @@
 #include "gemm.cuh"
 
 #define DEN_KMAX 64  // max ODE steps per call
+#define DEN_GRAPH_MAXB 64  // sampler calls up to this batch are launch-latency bound: replayed as CUDA graphs
 
 // ------------------------------------------------------------------------------------------
 // packed parameters
@@ -76,6 +77,17 @@ struct dt_denoiser {
   int film_time_K = 0;         // schedule the table currently holds (film_times)
   void* film_time_stream = nullptr;
   float film_time_ts[64];
+  // CUDA graphs of small-batch sampler calls (dt_fm_sample): static input / output buffers + one executable
+  // graph per (B, K, schedule, un-normalise) key; a key runs eagerly once (first-use initialisation is not
+  // capturable), is captured on its second call and replayed afterwards
+  float* g_noise = nullptr;    // [GB][T][A]
+  float* g_cond = nullptr;     // [GB][G]
+  __nv_bfloat16* g_lm = nullptr;  // [GB][NM][NM]
+  float* g_out = nullptr;      // [GB][T][A]
+  struct GraphEntry { int B, K; unsigned ebits; int norm; int state; /* 0 seen once, 1 graph, -1 not capturable */
+                      cudaGraphExec_t exec; long long launches; };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
   float* norm_dev = nullptr;   // [2 A] action mean / std on the device, cached (dt_fm_sample)
   float norm_host[16];
   bool norm_valid = false;
@@ -535,6 +547,9 @@ static TT* arena(dt_denoiser* d, size_t n, bool* ok) {
 
 void dt_denoiser_free(dt_ctx* ctx) {
   if (!ctx || !ctx->den) return;
+  for (auto& g : ctx->den->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (ctx->den->cap_stream) cudaStreamDestroy(ctx->den->cap_stream);
   for (void* p : ctx->den->allocs) cudaFree(p);
   delete ctx->den;
   ctx->den = nullptr;
@@ -721,6 +736,10 @@ extern "C" int dt_load_denoiser(dt_ctx* ctx, const dt_tensor_desc* tensors, int 
   d->film_time = arena<float>(d, (size_t)DEN_KMAX * d->F, &aok);
   d->mish_t = arena<float>(d, (size_t)DEN_KMAX * 256, &aok);
   d->norm_dev = arena<float>(d, 16, &aok);
+  d->g_noise = arena<float>(d, (size_t)DEN_GRAPH_MAXB * T * A, &aok);
+  d->g_out = arena<float>(d, (size_t)DEN_GRAPH_MAXB * T * A, &aok);
+  d->g_cond = arena<float>(d, (size_t)DEN_GRAPH_MAXB * G, &aok);
+  d->g_lm = arena<bf>(d, (size_t)DEN_GRAPH_MAXB * NM * NM, &aok);
   d->cond_in = arena<bf>(d, MB * d->kc_pad, &aok);
   const int oh1 = (NM + 6 - 7) / 2 + 1;
   const int ph = (oh1 + 2 - 3) / 2 + 1;
@@ -1041,11 +1060,12 @@ static int film_candidates(dt_ctx* ctx, dt_denoiser* d, const float* emb, int em
   return dt_conv_gemm(ctx, g, st);
 }
 
-static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, cudaStream_t st) {
+static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, cudaStream_t st, bool force = false) {
   // The per-step FiLM table depends only on the timesteps and the weights: an unchanged schedule (every call
   // of a planner run) reuses the table of the previous call -- stream order makes that safe on one stream;
   // a different stream recomputes.
-  if (d->film_time_K == K && d->film_time_stream == (void*)st && memcmp(d->film_time_ts, ts_host, K * sizeof(float)) == 0)
+  if (!force && d->film_time_K == K && d->film_time_stream == (void*)st &&
+      memcmp(d->film_time_ts, ts_host, K * sizeof(float)) == 0)
     return DT_OK;
   TimeSteps ts;
   memset(&ts, 0, sizeof(ts));
@@ -1104,6 +1124,31 @@ extern "C" int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* em
   return DT_OK;
 }
 
+// encoder once, per-candidate FiLM once, then K Euler steps of the U-Net (fm_policy.py:183-194)
+static int fm_sample_body(dt_ctx* ctx, dt_denoiser* d, const float* noise, const float* cond, const __nv_bfloat16* lm,
+                          int64_t B, int K, const float* ts, const float* dt, const float* d_norm, float* actions_out,
+                          cudaStream_t st, bool force_film_times) {
+  int rc = film_times(ctx, d, ts, K, st, force_film_times);
+  if (rc) return rc;
+  for (int64_t b0 = 0; b0 < B; b0 += d->MB) {
+    const int64_t nb = (B - b0 < d->MB) ? (B - b0) : d->MB;
+    const int64_t rows = nb * d->T;
+    float* a = actions_out + b0 * d->T * d->A;
+    if ((rc = encoder_forward(ctx, d, lm + b0 * d->NM * d->NM, nb, st))) return rc;
+    if ((rc = film_candidates(ctx, d, d->emb, d->emb_pad, cond + b0 * d->G, nb, st))) return rc;
+    DT_CUDA(cudaMemcpyAsync(a, noise + b0 * d->T * d->A, rows * d->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < K; ++k) {
+      k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(a, rows, d->A, d->X);
+      DT_LAUNCH_CHECK("k_prep_sample");
+      if ((rc = unet_body(ctx, d, nb, d->film_time + (size_t)k * d->F, st))) return rc;
+      if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k], a, nullptr,
+                                   (k == K - 1) ? d_norm : nullptr, st)))
+        return rc;
+    }
+  }
+  return DT_OK;
+}
+
 extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, const void* local_map, int64_t B,
                             int K, double exp_scale, const double* norm_host, float* actions_out, void* stream) {
   NEED_MODEL();
@@ -1129,10 +1174,9 @@ extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, 
       ts[k] = t0[k] * 20.0f;
     }
   }
-  int rc = film_times(ctx, d, ts, K, st);
-  if (rc) return rc;
   // un-normalisation constants: uploaded only when they change (then synchronously: the staging array is on
   // this stack frame); the steady state of a planner run enqueues without any host-device synchronisation
+  int rc;
   float* d_norm = nullptr;
   if (norm_host) {
     float hn[16];
@@ -1146,21 +1190,61 @@ extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, 
     }
   }
   const __nv_bfloat16* lm = (const __nv_bfloat16*)local_map;
-  for (int64_t b0 = 0; b0 < B; b0 += d->MB) {
-    const int64_t nb = (B - b0 < d->MB) ? (B - b0) : d->MB;
-    const int64_t rows = nb * d->T;
-    float* a = actions_out + b0 * d->T * d->A;
-    if ((rc = encoder_forward(ctx, d, lm + b0 * d->NM * d->NM, nb, st))) return rc;
-    if ((rc = film_candidates(ctx, d, d->emb, d->emb_pad, cond + b0 * d->G, nb, st))) return rc;
-    DT_CUDA(cudaMemcpyAsync(a, noise + b0 * d->T * d->A, rows * d->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    for (int k = 0; k < K; ++k) {
-      k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(a, rows, d->A, d->X);
-      DT_LAUNCH_CHECK("k_prep_sample");
-      if ((rc = unet_body(ctx, d, nb, d->film_time + (size_t)k * d->F, st))) return rc;
-      if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k], a, nullptr,
-                                   (k == K - 1) ? d_norm : nullptr, st)))
-        return rc;
+
+  // ---- small batches: one CUDA graph launch instead of ~100 K kernel launches ----
+  static const bool graphs_on = [] { const char* e = getenv("DITREE_GRAPHS"); return !(e && e[0] == '0'); }();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  // (not for nets whose widest GroupNorm takes the scratch-buffer fallback: that scratch may be re-allocated)
+  if (graphs_on && B <= DEN_GRAPH_MAXB && B <= d->MB && !ctx->prof_on && d->C[2] / 8 <= 256 &&
+      (st == nullptr || (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone))) {
+    unsigned ebits;
+    const float es = (float)exp_scale;
+    memcpy(&ebits, &es, 4);
+    dt_denoiser::GraphEntry* ge = nullptr;
+    for (auto& g : d->graphs)
+      if (g.B == (int)B && g.K == K && g.ebits == ebits && g.norm == (d_norm != nullptr)) ge = &g;
+    if (!ge) {  // first call with this key: eager (runs first-use initialisation), remembered
+      d->graphs.push_back(dt_denoiser::GraphEntry{(int)B, K, ebits, d_norm != nullptr, 0, nullptr, 0});
+    } else if (ge->state >= 0) {
+      const size_t na = (size_t)B * d->T * d->A;
+      DT_CUDA(cudaMemcpyAsync(d->g_noise, noise, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      DT_CUDA(cudaMemcpyAsync(d->g_cond, cond, (size_t)B * d->G * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      DT_CUDA(cudaMemcpyAsync(d->g_lm, lm, (size_t)B * d->NM * d->NM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+      if (ge->state == 0) {
+        const long long l0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot be
+        // captured); the instantiated graph is then launched into the caller's stream
+        if (!d->cap_stream) cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking);
+        bool ok = d->cap_stream && cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+          rc = fm_sample_body(ctx, d, d->g_noise, d->g_cond, d->g_lm, B, K, ts, dt, d_norm, d->g_out, d->cap_stream, true);
+          const cudaError_t e = cudaStreamEndCapture(d->cap_stream, &graph);
+          ok = (rc == DT_OK) && (e == cudaSuccess) && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        ge->launches = ctx->launches - l0;
+        ctx->launches = l0;
+        if (!ok) {
+          cudaGetLastError();
+          ge->state = -1;  // not capturable here: stay eager
+          ge->exec = nullptr;
+        } else {
+          ge->state = 1;
+        }
+      }
+      if (ge->state == 1) {
+        DT_CUDA(cudaGraphLaunch(ge->exec, st));
+        ctx->launches += ge->launches;
+        // the graph recomputed the per-step FiLM table for ITS schedule: record what the table now holds
+        d->film_time_K = K;
+        d->film_time_stream = (void*)st;
+        memcpy(d->film_time_ts, ts, K * sizeof(float));
+        DT_CUDA(cudaMemcpyAsync(actions_out, d->g_out, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return DT_OK;
+      }
     }
   }
-  return DT_OK;
+  return fm_sample_body(ctx, d, noise, cond, lm, B, K, ts, dt, d_norm, actions_out, st, false);
 }

@@ -790,10 +790,11 @@ template <int BN, int EPI, int GW, int CG>
 static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                           const GemmDev& d, cudaStream_t st) {
   using P = SmemPlan<BN, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;  // one bit per device: the attribute is per device
+  const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+  if (!(attr_set & dev_bit)) {
     DT_CUDA(cudaFuncSetAttribute(k_conv_gemm<BN, EPI, GW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
-    attr_set = true;
+    attr_set |= dev_bit;
   }
   const int unit_tiles = ((d.num_m_tiles + CG - 1) / CG) * d.num_n_tiles;
   const int max_units = ctx->sm_count / CG;  // persistent: one CTA (or CTA pair) per SM (pair)

@@ -28,7 +28,6 @@
 #else
 #define PROP_ST(p, v) (*(p) = (v))
 #endif
-#define PROP_WARPS (PROP_THREADS / 32)
 
 struct PropArgs {
   const float* state0;

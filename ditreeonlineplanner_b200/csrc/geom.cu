@@ -102,8 +102,27 @@ k_collide_ant(MapView m, const float* __restrict__ st, int64_t row_stride, int64
 // -------------------------------------------------------------------------------------------
 struct Axis {
   double v[32];  // linspace(-L/2 + scale/2, L/2 - scale/2, N), N <= 32
+  float startf, stepf;  // fp32 start / step of the same linspace (fast path: v[k] ~ startf + k stepf)
+  float amax;    // max |v|
 };
 
+// exact cell of one local-map point, as the float64 reference computes it
+__device__ __forceinline__ int local_map_cell_exact(const MapView& m, double cs, double sn, double px, double py,
+                                                    double cx, double cy, double xl, double yl) {
+  const double xg = xadd(xsub(xmul(cs, xl), xmul(sn, yl)), px);
+  const double yg = xadd(xadd(xmul(sn, xl), xmul(cs, yl)), py);
+  int yi = dt_floor_i(xdiv(xsub(cy, yg), m.s));
+  int xi = dt_floor_i(xdiv(xadd(xg, cx), m.s));
+  xi = dt_clampi(xi, 0, m.cols - 1);
+  yi = dt_clampi(yi, 0, m.rows - 1);
+  return yi * m.cols + xi;
+}
+
+// Fast path: the rotated / shifted grid coordinates in fp32, trusted when they are farther than `eps` from
+// every cell border that can change the clipped index (integers 1 .. dim-1); otherwise the float64 code
+// decides that point.  eps bounds the fp32 error per pose: five roundings of magnitude <= |x| + |y| + L +
+// (cols + rows) s / 2, each <= 2^-24 of it, plus the fp32 rounding of sin / cos / axis values (<= 2^-24
+// relative each, times |axis| <= L / 2), divided by the cell size -- with a factor 2 of slack.
 template <typename OutT>
 __global__ void __launch_bounds__(GEOM_THREADS)
 k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
@@ -114,28 +133,66 @@ k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y,
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const double cx = xmul(xdiv((double)m.cols, 2.0), m.s), cy = xmul(xdiv((double)m.rows, 2.0), m.s);
+  const float cxf = (float)cx, cyf = (float)cy, inv_s = (float)(1.0 / m.s);
+  const uint32_t s_map_u = dt_smem_u32(s_map);
+  const float cy2 = (float)(cy / m.s + 2.0), cx2 = (float)(cx / m.s + 2.0);
+  const float span = (float)(cx + cy) + 2.0f * ax.amax;
+  const float rmax = (float)m.rows, cmax = (float)m.cols;
   for (int64_t b = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); b < B;
        b += (int64_t)gridDim.x * warps_per_block) {
+    const float pxf = x[b * stride], pyf = y[b * stride], thf = th[b * stride];
+    const double px = (double)pxf, py = (double)pyf;
+    // fast path: libm's fp32 sincosf (<= 2 ulp); the float64 pair is computed only if some point needs it
+    float snf, csf;
+    sincosf(thf, &snf, &csf);
     double sn = 0.0, cs = 0.0;
-    if (lane == 0) sincos((double)th[b * stride], &sn, &cs);
-    sn = __shfl_sync(0xffffffffu, sn, 0);
-    cs = __shfl_sync(0xffffffffu, cs, 0);
-    const double px = (double)x[b * stride], py = (double)y[b * stride];
+    bool have_exact_trig = false;
+    const float eps = 2.0f * 5.9604645e-8f * 12.0f * (fabsf(pxf) + fabsf(pyf) + span) * inv_s + 1.0e-7f;
+    // non-finite poses or an eps that swallows a cell: everything through the exact code
+    const bool fast_ok = eps < 0.25f;
     OutT* o = out + b * (int64_t)(N * N);
+    int i = lane / N, j = lane - i * N;  // out[i, j] uses ys[i], xs[j]; advanced incrementally (no division)
     for (int p = lane; p < N * N; p += 32) {
-      const int i = p / N, j = p - i * N;  // out[i, j] uses ys[i], xs[j]
-      const double xl = ax.v[j], yl = ax.v[i];
-      const double xg = xadd(xsub(xmul(cs, xl), xmul(sn, yl)), px);
-      const double yg = xadd(xadd(xmul(sn, xl), xmul(cs, yl)), py);
-      int yi = dt_floor_i(xdiv(xsub(cy, yg), m.s));
-      int xi = dt_floor_i(xdiv(xadd(xg, cx), m.s));
-      xi = dt_clampi(xi, 0, m.cols - 1);
-      yi = dt_clampi(yi, 0, m.rows - 1);
-      const float occ = (float)s_map[yi * m.cols + xi];
+      int cell;
+      bool exact = !fast_ok;
+      if (fast_ok) {
+        // axis values arithmetically (an indexed constant-bank load per point stalls the FMA chain): within
+        // 1 ulp of float(linspace), covered by eps
+        const float xl = fmaf((float)j, ax.stepf, ax.startf), yl = fmaf((float)i, ax.stepf, ax.startf);
+        const float xg = fmaf(csf, xl, fmaf(-snf, yl, pxf));
+        const float yg = fmaf(snf, xl, fmaf(csf, yl, pyf));
+        // grid coordinates shifted by +2 and clamped half a cell outside the map: floor by a round-down add
+        // of 2^23 (the integer lands in the mantissa; no conversion instructions), in-cell offset exact
+        const float M23 = 8388608.0f;
+        const float u = fminf(fmaxf(fmaf(-yg, inv_s, cy2), 1.5f), rmax + 2.5f);
+        const float w = fminf(fmaxf(fmaf(xg, inv_s, cx2), 1.5f), cmax + 2.5f);
+        const float tu = __fadd_rd(u, M23), tw = __fadd_rd(w, M23);
+        const float du = u - (tu - M23), dw = w - (tw - M23);
+        // any cell border closer than eps sends the point to the float64 code
+        exact = fminf(fminf(du, 1.0f - du), fminf(dw, 1.0f - dw)) < eps;
+        const int yi = min(max(__float_as_int(tu) - (0x4B000000 + 2), 0), m.rows - 1);
+        const int xi = min(max(__float_as_int(tw) - (0x4B000000 + 2), 0), m.cols - 1);
+        cell = yi * m.cols + xi;
+      }
+      if (exact) {
+        if (!have_exact_trig) {
+          sincos((double)thf, &sn, &cs);
+          have_exact_trig = true;
+        }
+        cell = local_map_cell_exact(m, cs, sn, px, py, cx, cy, ax.v[j], ax.v[i]);
+      }
+      uint32_t occ_u;
+      asm("ld.shared.u8 %0, [%1];" : "=r"(occ_u) : "r"(s_map_u + (uint32_t)cell));
+      const float occ = (float)occ_u;
       if (sizeof(OutT) == 4) {
         o[p] = (OutT)occ;
       } else {
         o[p] = (OutT)(occ * 2.0f - 1.0f);  // sampler's rescale to [-1, 1] (fm_policy.py:152)
+      }
+      j += 32;
+      while (j >= N) {
+        j -= N;
+        ++i;
       }
     }
   }
@@ -383,6 +440,11 @@ extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const f
     }
     ax.v[N - 1] = stop;
     for (int i = N; i < 32; ++i) ax.v[i] = 0.0;
+    ax.amax = 0.f;
+    for (int i = 0; i < 32; ++i)
+      if (fabs(ax.v[i]) > ax.amax) ax.amax = (float)fabs(ax.v[i]) * 1.000001f;
+    ax.startf = (float)start;
+    ax.stepf = (float)step;
   }
   MapView m = dt_map_view(ctx);
   const int warps = GEOM_THREADS / 32;

@@ -280,7 +280,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rows_t = np.array(list(table.values()))
         suite = {"units": len(table), "scenarios_per_s": len(table) / float(t.item()), "seconds": float(t.item()),
-                 "unit": "one (scenario, run) of test_scenarios_car: batched RRT with continuous slot refill, 2 x 256 slots, "
+                 "unit": "one (scenario, run) of test_scenarios_car: batched RRT with continuous slot refill, 2 x 256 slots on two streams, "
                          "4096 chunk expansions (the reference's iteration count) or goal, K=1 (the reference's "
                          "planning_diffusion_iters), large denoiser",
                  "mean_tree_nodes": float(np.mean(rows_t[:, 6][rows_t[:, 6] > 0])) if (rows_t[:, 6] > 0).any() else 0.0,

@@ -133,7 +133,7 @@ k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y,
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const double cx = xmul(xdiv((double)m.cols, 2.0), m.s), cy = xmul(xdiv((double)m.rows, 2.0), m.s);
-  const float cxf = (float)cx, cyf = (float)cy, inv_s = (float)(1.0 / m.s);
+  const float inv_s = (float)(1.0 / m.s);
   const uint32_t s_map_u = dt_smem_u32(s_map);
   const float cy2 = (float)(cy / m.s + 2.0), cx2 = (float)(cx / m.s + 2.0);
   const float span = (float)(cx + cy) + 2.0f * ax.amax;

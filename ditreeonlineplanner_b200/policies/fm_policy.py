@@ -70,6 +70,22 @@ class DiffusionSampler(nn.Module):
             self._ctx = ctx
         return self._ctx
 
+    def _twin_context(self, max_batch):
+        """A second device context holding the same packed weights (own activation arena), so two independent
+        sampler passes can run concurrently on two streams (the continuous-refill planner's two slot groups)."""
+        twin = getattr(self, "_twin", None)
+        if twin is None or self._twin_batch < max_batch:
+            from ..runtime import Context
+            main = self._context()
+            if twin is not None:
+                twin.close()
+            twin = Context(main.device.index)
+            dims, emb, cond_dim, A = _infer_cfg(self._state_dict)
+            twin.load_denoiser(self._state_dict, action_dim=A, horizon=self.pred_horizon, cond_dim=cond_dim, emb_dim=emb,
+                               map_size=int(self.local_map_size), down_dims=dims, max_batch=int(max_batch))
+            self._twin, self._twin_batch = twin, int(max_batch)
+        return self._twin
+
     def _check_supported(self):
         if self.policy != "flow_matching":
             raise NotImplementedError("only the flow_matching policy runs on the B200 path")

@@ -270,10 +270,13 @@ def main():
         from ditreeonlineplanner_b200 import scenarios as sc
         from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
         invalidate_staged_map()
+        suite_kw = {"batch_size": 256, "iteration_cap": 256 * 8 * 2}
+        # untimed warm-up unit: builds the planner's second device context, captures its graphs
+        sc.run_car_unit(sc.load_scenarios("test_scenarios_car")[0], 0, 0, sampler, 1e9, suite_kw)
         barrier()
         t0 = time.perf_counter()
         table, _ = sc.run_suite(sampler, total_runs=args.suite_runs, time_budget=1e9, rank=rank, world=world,
-                                device=ctx.device, planner_kwargs={"batch_size": 256, "iteration_cap": 256 * 8 * 2})
+                                device=ctx.device, planner_kwargs=suite_kw)
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:

@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--maze", default="boxes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suite", action="store_true", help="skip the scenario-suite (scenarios/s) leg")
-    ap.add_argument("--suite-runs", type=int, default=8, help="runs per scenario in the suite leg (15 x runs units)")
+    ap.add_argument("--suite-runs", type=int, default=10, help="runs per scenario in the suite leg (15 x runs units; 10 = the reference's total_runs)")
     ap.add_argument("--prop-batch", type=int, default=1 << 20, help="candidates for the propagate+collide roofline leg")
     return ap.parse_args()
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "dt_ctx_destroy": (None, [c_p]),
     "dt_last_error": (C.c_char_p, [c_p]),
     "dt_version": (C.c_char_p, []),
+    "dt_set_option": (C.c_int, [c_p, C.c_char_p, C.c_int]),
     "dt_set_map": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_float, c_p]),
     "dt_collide_car": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dt_collide_points": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, C.c_double, C.c_double, c_p, c_p]),

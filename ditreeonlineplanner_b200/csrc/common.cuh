@@ -38,6 +38,8 @@ struct dt_ctx {
   size_t scratch_bytes = 0;
   void* d_wide = nullptr;  // fp32 pre-normalisation scratch of the wide-GroupNorm GEMM fallback (gemm.cu)
   size_t wide_bytes = 0;
+  void* d_splitk = nullptr;   // fixed-size fp32 scratch of the split-K path (gemm.cu)
+  bool splitk_on = true;      // dt_set_option(ctx, "splitk", 0) restores batch-size independent bits
   int64_t launches = 0;
   int sm_count = 148;
   dt_denoiser* den = nullptr;

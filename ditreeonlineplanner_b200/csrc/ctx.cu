@@ -43,8 +43,18 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_wide) cudaFree(ctx->d_wide);
+  if (ctx->d_splitk) cudaFree(ctx->d_splitk);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   delete ctx;
+}
+
+extern "C" int dt_set_option(dt_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return DT_E_ARG;
+  if (strcmp(name, "splitk") == 0) {
+    ctx->splitk_on = value != 0;
+    return DT_OK;
+  }
+  return dt_fail(ctx, DT_E_ARG, "dt_set_option: unknown option");
 }
 
 extern "C" const char* dt_last_error(dt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }

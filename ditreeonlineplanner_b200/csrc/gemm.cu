@@ -223,6 +223,10 @@ struct GemmDev {
   __nv_bfloat16* out_bf16;
   float* out_f32;
   long long ldc, out_b_stride, out_t_stride, out_off;
+  // split-K (small problems): a tile index also names a K slice of kb_per_slice 64-deep blocks; slice s writes
+  // its partial sums slice_rows output rows further down (plain epilogue, fp32, reduced by k_splitk_epi)
+  int ksplit, kb_per_slice;
+  long long slice_rows;
 };
 
 template <int BN, int CG>
@@ -305,14 +309,17 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 
   // tiles are (unit-level M tile, N tile); a unit-level M tile is CG * 128 rows, CTA `rank` owns its 128-row slice
   const int unit_m_tiles = (g.num_m_tiles + CG - 1) / CG;
-  const int total_tiles = unit_m_tiles * g.num_n_tiles;
+  const int total_tiles = unit_m_tiles * g.num_n_tiles * g.ksplit;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units) {
-      const int um_tile = tile / g.num_n_tiles, n_tile = tile - um_tile * g.num_n_tiles;
+      const int slice = tile % g.ksplit, tl = tile / g.ksplit;
+      const int kb0 = slice * g.kb_per_slice;
+      const int kb1 = (kb0 + g.kb_per_slice < g.nkb_total) ? kb0 + g.kb_per_slice : g.nkb_total;
+      const int um_tile = tl / g.num_n_tiles, n_tile = tl - um_tile * g.num_n_tiles;
       const int m_tile = um_tile * CG + (int)rank;
       int b_base, t_base;
       if (g.tiles_per_sample > 0) {
@@ -327,6 +334,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         const GemmSeg sg = g.seg[s];
         const CUtensorMap* mA = sg.src ? &mapA1 : &mapA0;
         for (int blk = 0; blk < sg.nblk; ++blk, ++kw) {
+          if (kw < kb0 || kw >= kb1) continue;  // another K slice's block
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (lane == 0) {
             const uint32_t sa = base + stage * P::kStage;
@@ -360,10 +368,12 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     uint32_t acc_phase = 0;
     if (rank == 0) {
       for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const int kb0_ = (tile % g.ksplit) * g.kb_per_slice;
+        const int nkb = ((kb0_ + g.kb_per_slice < g.nkb_total) ? kb0_ + g.kb_per_slice : g.nkb_total) - kb0_;
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < g.nkb_total; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           if (lane == 0) {
@@ -378,10 +388,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             // free the smem slot (in both CTAs) when these MMAs retire; publish the accumulator after the last block
             if (CG == 2) {
               tc2_commit(bar_empty + 8 * stage);
-              if (kb == g.nkb_total - 1) tc2_commit(bar_tfull + 8 * acc);
+              if (kb == nkb - 1) tc2_commit(bar_tfull + 8 * acc);
             } else {
               tc_commit(bar_empty + 8 * stage);
-              if (kb == g.nkb_total - 1) tc_commit(bar_tfull + 8 * acc);
+              if (kb == nkb - 1) tc_commit(bar_tfull + 8 * acc);
             }
           }
           __syncwarp();
@@ -420,7 +430,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     static_assert(NG <= 8, "red[] holds 8 groups per warp");
     float pf_par[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     float pf_film[PF];
-    auto prefetch = [&](int tile_) {
+    auto prefetch = [&](int tile_k) {
+      const int tile_ = tile_k / g.ksplit;  // drop the K slice
       const int um_ = tile_ / g.num_n_tiles, n0_ = (tile_ - um_ * g.num_n_tiles) * BN;
       const int m_ = um_ * CG + (int)rank;
       pf_par[0] = g.bias ? __ldg(g.bias + n0_ + pcol) : 0.f;
@@ -446,7 +457,8 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
-      const int um_tile = tile / g.num_n_tiles, n_tile = tile - um_tile * g.num_n_tiles;
+      const int slice = tile % g.ksplit, tl = tile / g.ksplit;
+      const int um_tile = tl / g.num_n_tiles, n_tile = tl - um_tile * g.num_n_tiles;
       const int m_tile = um_tile * CG + (int)rank;
       const int n0 = n_tile * BN;
       long long b;
@@ -483,7 +495,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
-      const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off;
+      const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off + slice * g.slice_rows;
       const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
 
       // GroupNorm groups seen by this warp's column slice: NLG whole groups when a group fits in the
@@ -796,7 +808,7 @@ static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap&
     DT_CUDA(cudaFuncSetAttribute(k_conv_gemm<BN, EPI, GW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     attr_set |= dev_bit;
   }
-  const int unit_tiles = ((d.num_m_tiles + CG - 1) / CG) * d.num_n_tiles;
+  const int unit_tiles = ((d.num_m_tiles + CG - 1) / CG) * d.num_n_tiles * d.ksplit;
   const int max_units = ctx->sm_count / CG;  // persistent: one CTA (or CTA pair) per SM (pair)
   const int units = unit_tiles < max_units ? unit_tiles : max_units;
   cudaLaunchConfig_t cfg;
@@ -948,10 +960,150 @@ static int conv_gemm_wide_gn(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   return DT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split-K for small problems (at most 128 rows: the reference's own B = 1 planning loop).  With one M tile a
+// layer keeps only N / BN = 2..8 CTAs busy and each streams its whole weight slab alone (35-50 us per layer
+// although the weights could cross HBM in a few us).  The tile scheduler therefore also splits K: every
+// (N tile, K slice) pair is a work item of the same tcgen05 kernel (plain epilogue, fp32 partial sums of slice s
+// written slice_rows rows further down a scratch buffer), and k_splitk_epi sums the slices, adds the bias
+// and applies the epilogue the fused kernel would have applied: GroupNorm -> Mish -> FiLM (+ residual) per
+// (sample, group), or bias (+ residual, ReLU), with the same output addressing.
+// ---------------------------------------------------------------------------------------------
+struct SplitKEpi {
+  const float* part;  // [S][rows][N]
+  int S, rows, T, N, gw, epi, relu;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* film;
+  long long film_ld;
+  const float* film_t;
+  const __nv_bfloat16* resid;
+  long long ld_res;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  long long ldc, out_b_stride, out_t_stride, out_off;
+};
+
+// one block per (sample, window of `gw` columns): a GroupNorm group (EPI_GN_MISH) or a slab of columns
+#define SPLITK_EPI_THREADS 1024
+
+__global__ void __launch_bounds__(SPLITK_EPI_THREADS)
+k_splitk_epi(SplitKEpi p) {
+  extern __shared__ __align__(16) float s_y[];  // [T][gw]
+  __shared__ float s_a[SPLITK_EPI_THREADS], s_b[SPLITK_EPI_THREADS];
+  const int windows = p.N / p.gw;
+  const int b = blockIdx.x / windows, n0 = (blockIdx.x % windows) * p.gw;
+  const int cnt = p.T * p.gw;
+  float s = 0.f, ss = 0.f;
+  const long long kstride = (long long)p.rows * p.N;
+  for (int i = threadIdx.x; i < cnt; i += SPLITK_EPI_THREADS) {
+    const int t = i / p.gw, c = i - t * p.gw, n = n0 + c;
+    const float* q = p.part + (long long)(b * p.T + t) * p.N + n;
+    // four independent partial sums (fixed order): the S slice reads of an element are in flight together
+    float v0 = p.bias ? p.bias[n] : 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= p.S; k += 4) {
+      v0 += __ldg(q + (k + 0) * kstride);
+      v1 += __ldg(q + (k + 1) * kstride);
+      v2 += __ldg(q + (k + 2) * kstride);
+      v3 += __ldg(q + (k + 3) * kstride);
+    }
+    for (; k < p.S; ++k) v0 += __ldg(q + k * kstride);
+    const float v = (v0 + v1) + (v2 + v3);
+    s_y[i] = v;
+    s += v;
+    ss += v * v;
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (p.epi == EPI_GN_MISH) {
+    s_a[threadIdx.x] = s;
+    s_b[threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = SPLITK_EPI_THREADS / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        s_a[threadIdx.x] += s_a[threadIdx.x + o];
+        s_b[threadIdx.x] += s_b[threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    mean = s_a[0] / (float)cnt;
+    rstd = rsqrtf(fmaxf(s_b[0] / (float)cnt - mean * mean, 0.f) + 1e-5f);
+  }
+  for (int i = threadIdx.x; i < cnt; i += SPLITK_EPI_THREADS) {  // a thread revisits the elements it wrote itself
+    const int t = i / p.gw, c = i - t * p.gw, n = n0 + c;
+    float v = s_y[i];
+    if (p.epi == EPI_GN_MISH) {
+      v = mish_f((v - mean) * rstd * p.gamma[n] + p.beta[n]);
+      if (p.film) {
+        const float sc = p.film[(long long)b * p.film_ld + n] + (p.film_t ? p.film_t[n] : 0.f);
+        const float sh = p.film[(long long)b * p.film_ld + p.N + n] + (p.film_t ? p.film_t[p.N + n] : 0.f);
+        v = v * sc + sh;
+      }
+    }
+    const long long row = (long long)b * p.out_b_stride + (long long)t * p.out_t_stride + p.out_off;
+    if (p.resid) v += __bfloat162float(p.resid[row * p.ld_res + n]);
+    if (p.epi == EPI_PLAIN && p.relu) v = fmaxf(v, 0.f);
+    if (p.out_bf16) p.out_bf16[row * p.ldc + n] = __float2bfloat16(v);
+    if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
+  }
+}
+
+#define SPLITK_SCRATCH_BYTES (48u << 20)
+
+int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);
+
+// -> 0 = not applicable (caller continues with the fused path), 1 = done, negative = error
+static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
+  if (!ctx->splitk_on || ctx->prof_on || g.ksplit > 1 || g.T > 64 || g.B * g.T > 128 || 128 % g.T != 0) return 0;
+  long long nkb = 0;
+  for (int s = 0; s < g.nseg; ++s) nkb += g.seg[s].nblk;
+  const int rows = (int)(g.B * g.T);
+  const int bn = (g.N % 256 == 0) ? 256 : ((g.N % 128 == 0) ? 128 : 64);
+  const int n_tiles = g.N / bn;
+  if (nkb < 8 || n_tiles * 4 > ctx->sm_count) return 0;
+  int ksplit = ctx->sm_count / n_tiles;              // one work item per SM
+  if (ksplit > nkb / 2) ksplit = (int)(nkb / 2);     // at least two K blocks per item
+  if (ksplit < 2) return 0;
+  const int per = (int)((nkb + ksplit - 1) / ksplit);
+  ksplit = (int)((nkb + per - 1) / per);             // no empty slice
+  if (g.epi == EPI_GN_MISH && (g.group_width < 8 || g.N % g.group_width != 0 || g.group_width * g.T > 16384)) return 0;
+  if ((size_t)ksplit * rows * g.N * sizeof(float) > SPLITK_SCRATCH_BYTES) return 0;
+  if (!ctx->d_splitk) {  // fixed size, allocated once: the pointer is baked into captured graphs
+    DT_CUDA(cudaMalloc(&ctx->d_splitk, SPLITK_SCRATCH_BYTES));
+    DT_CUDA(cudaFuncSetAttribute(k_splitk_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
+  }
+  ConvGemm part = g;
+  part.epi = EPI_PLAIN;
+  part.bias = nullptr; part.gamma = part.beta = nullptr; part.film = part.film_t = nullptr;
+  part.resid = nullptr; part.relu = 0;
+  part.out_bf16 = nullptr;
+  part.out_f32 = (float*)ctx->d_splitk;
+  part.ldc = g.N; part.out_b_stride = g.T; part.out_t_stride = 1; part.out_off = 0;
+  part.ksplit = ksplit; part.kb_per_slice = per; part.slice_rows = rows;
+  int rc = dt_conv_gemm(ctx, part, st);
+  if (rc) return rc;
+  SplitKEpi e;
+  e.part = (const float*)ctx->d_splitk; e.S = ksplit; e.rows = rows; e.T = g.T; e.N = g.N; e.epi = g.epi; e.relu = g.relu;
+  e.gw = (g.epi == EPI_GN_MISH) ? g.group_width : 64;
+  e.bias = g.bias; e.gamma = g.gamma; e.beta = g.beta; e.film = g.film; e.film_ld = g.film_ld; e.film_t = g.film_t;
+  e.resid = g.resid; e.ld_res = g.ld_res; e.out_bf16 = g.out_bf16; e.out_f32 = g.out_f32;
+  e.ldc = g.ldc; e.out_b_stride = g.out_b_stride; e.out_t_stride = g.out_t_stride; e.out_off = g.out_off;
+  const int blocks = (int)(g.B * (g.N / e.gw));
+  k_splitk_epi<<<blocks, SPLITK_EPI_THREADS, (size_t)g.T * e.gw * sizeof(float), st>>>(e);
+  DT_LAUNCH_CHECK("k_splitk_epi");
+  return 1;
+}
+
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (g.B <= 0) return DT_OK;
   if (g.nseg < 1 || g.nseg > GEMM_MAX_SEG || !g.w || !g.a[0].ptr || g.N % 64 != 0)
     return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad problem description");
+  {
+    const int sk = conv_gemm_splitk(ctx, g, st);
+    if (sk < 0) return sk;
+    if (sk == 1) return DT_OK;
+  }
   if (g.epi == EPI_GN_MISH && g.group_width > 256) return conv_gemm_wide_gn(ctx, g, st);
   // tile geometry: a tile holds whole samples (T <= 128) or a 128-row slice of one sample
   int T = g.T, rows_t, nb, tps;
@@ -1007,6 +1159,9 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   d.resid = g.resid; d.ld_res = g.ld_res; d.relu = g.relu;
   d.out_bf16 = g.out_bf16; d.out_f32 = g.out_f32;
   d.ldc = g.ldc; d.out_b_stride = g.out_b_stride; d.out_t_stride = g.out_t_stride; d.out_off = g.out_off;
+  d.ksplit = g.ksplit > 1 ? g.ksplit : 1;
+  d.kb_per_slice = g.ksplit > 1 ? g.kb_per_slice : d.nkb_total;
+  d.slice_rows = g.slice_rows;
   if (!d.out_bf16 && !d.out_f32) return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: no output");
 
   CUtensorMap mA0, mA1, mW;

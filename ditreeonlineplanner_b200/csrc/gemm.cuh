@@ -51,6 +51,9 @@ struct ConvGemm {
   float* out_f32 = nullptr;
   int64_t ldc = 0;
   int64_t out_b_stride = 0, out_t_stride = 1, out_off = 0;
+  // ---- split-K (set by dt_conv_gemm itself for small problems; plain epilogue, fp32 partial sums) -------
+  int ksplit = 1, kb_per_slice = 0;
+  int64_t slice_rows = 0;
 };
 
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);

@@ -83,6 +83,9 @@ class Context:
     def launches(self):
         return int(self.lib.dt_launch_count(self.h))
 
+    def set_option(self, name, value):
+        self._check(self.lib.dt_set_option(self.h, name.encode(), int(value)))
+
     # -- map --------------------------------------------------------------------------------
     def set_map(self, grid, s_global=1.0):
         g = np.ascontiguousarray(np.asarray(grid, dtype=np.float32))

@@ -46,6 +46,12 @@ void dt_ctx_destroy(dt_ctx* ctx);
 const char* dt_last_error(dt_ctx* ctx);
 const char* dt_version(void);
 
+/* Tuning switches.  "splitk" (default 1): conv GEMMs with at most 128 rows (sampler batches of 1-2 candidates,
+ * the reference's own B = 1 loop) split K over all SMs and reduce in a second kernel -- ~2x less latency, but a
+ * candidate's bits then depend on whether it was sampled alone or in a batch (different fp32 summation order,
+ * same 2e-2 tolerance).  0 restores batch-size independent results. */
+int dt_set_option(dt_ctx* ctx, const char* name, int value);
+
 /* Occupancy grid upload.  Replaces RRT_Planner.update_maze / BasePlanner.maze
  * (planners/RRT.py:57-59, planners/base_planner.py:117).  grid_host: rows*cols floats, row-major,
  * cell value 1 = wall.  s_global = metres per cell (1 car, 4 ant). Synchronous on `stream`. */

@@ -997,23 +997,34 @@ k_splitk_epi(SplitKEpi p) {
   const int cnt = p.T * p.gw;
   float s = 0.f, ss = 0.f;
   const long long kstride = (long long)p.rows * p.N;
-  for (int i = threadIdx.x; i < cnt; i += SPLITK_EPI_THREADS) {
-    const int t = i / p.gw, c = i - t * p.gw, n = n0 + c;
-    const float* q = p.part + (long long)(b * p.T + t) * p.N + n;
-    // four independent partial sums (fixed order): the S slice reads of an element are in flight together
-    float v0 = p.bias ? p.bias[n] : 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-    int k = 0;
-    for (; k + 4 <= p.S; k += 4) {
-      v0 += __ldg(q + (k + 0) * kstride);
-      v1 += __ldg(q + (k + 1) * kstride);
-      v2 += __ldg(q + (k + 2) * kstride);
-      v3 += __ldg(q + (k + 3) * kstride);
+  // four elements per thread at a time, slices in ascending order per element (deterministic); the loop over
+  // slices is unrolled so 16 independent loads are in flight per thread
+  for (int i0 = threadIdx.x; i0 < cnt; i0 += 4 * SPLITK_EPI_THREADS) {
+    const float* q[4];
+    float v[4];
+    bool on[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i0 + e * SPLITK_EPI_THREADS;
+      on[e] = i < cnt;
+      const int ii = on[e] ? i : i0;
+      const int t = ii / p.gw, c = ii - t * p.gw, n = n0 + c;
+      q[e] = p.part + (long long)(b * p.T + t) * p.N + n;
+      v[e] = p.bias ? p.bias[n] : 0.f;
     }
-    for (; k < p.S; ++k) v0 += __ldg(q + k * kstride);
-    const float v = (v0 + v1) + (v2 + v3);
-    s_y[i] = v;
-    s += v;
-    ss += v * v;
+#pragma unroll 4
+    for (int k = 0; k < p.S; ++k) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] += __ldg(q[e] + k * kstride);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (on[e]) {
+        s_y[i0 + e * SPLITK_EPI_THREADS] = v[e];
+        s += v[e];
+        ss += v[e] * v[e];
+      }
+    }
   }
   float mean = 0.f, rstd = 1.f;
   if (p.epi == EPI_GN_MISH) {

@@ -1,7 +1,8 @@
 // ctx.cu -- context lifetime, map upload, status word.
 #include "common.cuh"
 
-void dt_denoiser_free(dt_ctx* ctx);  // denoiser.cu
+void dt_denoiser_free(dt_ctx* ctx);         // denoiser.cu
+void dt_denoiser_drop_graphs(dt_ctx* ctx);  // denoiser.cu
 
 extern "C" const char* dt_version(void) { return "ditree-b200 0.1 (sm_100a)"; }
 
@@ -51,6 +52,11 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
 extern "C" int dt_set_option(dt_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return DT_E_ARG;
   if (strcmp(name, "splitk") == 0) {
+    if (ctx->splitk_on != (value != 0)) {
+      DT_CUDA(cudaSetDevice(ctx->device));
+      DT_CUDA(cudaDeviceSynchronize());  // no replay of a graph that is about to be destroyed may be in flight
+      dt_denoiser_drop_graphs(ctx);
+    }
     ctx->splitk_on = value != 0;
     return DT_OK;
   }

@@ -545,6 +545,14 @@ static TT* arena(dt_denoiser* d, size_t n, bool* ok) {
   return (TT*)p;
 }
 
+// captured sampler graphs bake in the kernel selection: dropped whenever an option that changes it is set
+void dt_denoiser_drop_graphs(dt_ctx* ctx) {
+  if (!ctx || !ctx->den) return;
+  for (auto& g : ctx->den->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->den->graphs.clear();
+}
+
 void dt_denoiser_free(dt_ctx* ctx) {
   if (!ctx || !ctx->den) return;
   for (auto& g : ctx->den->graphs)

@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "gemm.cuh"
 
 #define BM 128
@@ -986,15 +988,25 @@ struct SplitKEpi {
 };
 
 // one block per (sample, window of `gw` columns): a GroupNorm group (EPI_GN_MISH) or a slab of columns
-#define SPLITK_EPI_THREADS 1024
+#define SPLITK_EPI_THREADS 256
 
+// A cluster of CS CTAs per (sample, window of `gw` columns) -- a GroupNorm group (EPI_GN_MISH) or a slab of
+// columns -- each CTA owning T / CS rows: the slice sums are pulled by CS times more SMs than one CTA per
+// window could use (the kernel is bound by each SM's L2 read rate), the group statistics are exchanged
+// through distributed shared memory.
 __global__ void __launch_bounds__(SPLITK_EPI_THREADS)
 k_splitk_epi(SplitKEpi p) {
-  extern __shared__ __align__(16) float s_y[];  // [T][gw]
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  extern __shared__ __align__(16) float s_y[];  // [T / CS][gw]
   __shared__ float s_a[SPLITK_EPI_THREADS], s_b[SPLITK_EPI_THREADS];
+  __shared__ float s_part[2];
+  const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int win = blockIdx.x / CS;
   const int windows = p.N / p.gw;
-  const int b = blockIdx.x / windows, n0 = (blockIdx.x % windows) * p.gw;
-  const int cnt = p.T * p.gw;
+  const int b = win / windows, n0 = (win % windows) * p.gw;
+  const int t_rows = p.T / CS, t_first = r * t_rows;
+  const int cnt = t_rows * p.gw;
   float s = 0.f, ss = 0.f;
   const long long kstride = (long long)p.rows * p.N;
   // four elements per thread at a time, slices in ascending order per element (deterministic); the loop over
@@ -1008,7 +1020,7 @@ k_splitk_epi(SplitKEpi p) {
       const int i = i0 + e * SPLITK_EPI_THREADS;
       on[e] = i < cnt;
       const int ii = on[e] ? i : i0;
-      const int t = ii / p.gw, c = ii - t * p.gw, n = n0 + c;
+      const int t = t_first + ii / p.gw, c = ii % p.gw, n = n0 + c;
       q[e] = p.part + (long long)(b * p.T + t) * p.N + n;
       v[e] = p.bias ? p.bias[n] : 0.f;
     }
@@ -1038,11 +1050,24 @@ k_splitk_epi(SplitKEpi p) {
       }
       __syncthreads();
     }
-    mean = s_a[0] / (float)cnt;
-    rstd = rsqrtf(fmaxf(s_b[0] / (float)cnt - mean * mean, 0.f) + 1e-5f);
+    if (threadIdx.x == 0) {
+      s_part[0] = s_a[0];
+      s_part[1] = s_b[0];
+    }
+    cluster.sync();  // every CTA's partial statistics are published
+    float ts = 0.f, tq = 0.f;
+    for (int k = 0; k < CS; ++k) {  // same order in every CTA: identical totals
+      const float* remote = cluster.map_shared_rank(s_part, k);
+      ts += remote[0];
+      tq += remote[1];
+    }
+    cluster.sync();  // nobody leaves (and frees its shared memory) while a peer may still read it
+    const float total = (float)(p.T * p.gw);
+    mean = ts / total;
+    rstd = rsqrtf(fmaxf(tq / total - mean * mean, 0.f) + 1e-5f);
   }
   for (int i = threadIdx.x; i < cnt; i += SPLITK_EPI_THREADS) {  // a thread revisits the elements it wrote itself
-    const int t = i / p.gw, c = i - t * p.gw, n = n0 + c;
+    const int t = t_first + i / p.gw, c = i % p.gw, n = n0 + c;
     float v = s_y[i];
     if (p.epi == EPI_GN_MISH) {
       v = mish_f((v - mean) * rstd * p.gamma[n] + p.beta[n]);
@@ -1100,8 +1125,23 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   e.bias = g.bias; e.gamma = g.gamma; e.beta = g.beta; e.film = g.film; e.film_ld = g.film_ld; e.film_t = g.film_t;
   e.resid = g.resid; e.ld_res = g.ld_res; e.out_bf16 = g.out_bf16; e.out_f32 = g.out_f32;
   e.ldc = g.ldc; e.out_b_stride = g.out_b_stride; e.out_t_stride = g.out_t_stride; e.out_off = g.out_off;
-  const int blocks = (int)(g.B * (g.N / e.gw));
-  k_splitk_epi<<<blocks, SPLITK_EPI_THREADS, (size_t)g.T * e.gw * sizeof(float), st>>>(e);
+  // cluster size: up to 8 CTAs per window, T / CS whole rows each
+  int cs = 8;
+  while (cs > 1 && g.T % cs != 0) cs >>= 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(g.B * (g.N / e.gw) * cs));
+  cfg.blockDim = dim3(SPLITK_EPI_THREADS);
+  cfg.dynamicSmemBytes = (size_t)(g.T / cs) * e.gw * sizeof(float);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DT_CUDA(cudaLaunchKernelEx(&cfg, k_splitk_epi, e));
   DT_LAUNCH_CHECK("k_splitk_epi");
   return 1;
 }

@@ -12,7 +12,7 @@ dims = UNET_DIMS["large"]
 ctx.load_denoiser(random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims), action_dim=2, horizon=64,
                   cond_dim=7, emb_dim=400, map_size=20, down_dims=dims, max_batch=4096)
 enc, unet = denoiser_flops(1, down_dims=dims)
-for B in (64, 256, 1024, 4096):
+for B in [int(b) for b in os.environ.get("SB_BATCHES", "64,256,1024,4096").split(",")]:
     st, prev = synth_candidates(grid, B, 1)
     st = torch.as_tensor(st).cuda(); prev = torch.as_tensor(prev).cuda()
     goal = torch.as_tensor(goal_of(grid).astype(np.float32)).cuda()

@@ -196,6 +196,45 @@ def test_tree_replay_matches_reference(mazes, monkeypatch):
     assert rel(path, g["path"]) < 1e-4 and rel(actions, g["actions"]) < 1e-6
 
 
+class _Prefixed:
+    """View of one scenario's entries ('{k}.name') of tree_scenarios.npz."""
+    def __init__(self, g, k):
+        self.g, self.pre = g, f"{k}."
+
+    def __getitem__(self, name):
+        return self.g[self.pre + name]
+
+
+@pytest.mark.parametrize("k", range(15))
+def test_tree_replay_every_scenario(k, monkeypatch):
+    """SURVEY 8c item 10 on every row of test_scenarios_car.csv: the reference's tree after 30 fake seconds
+    (113-145 iterations at B = 1, seeds 42), rebuilt with its sampled actions teacher-forced -- same sampler
+    inputs call by call (so the same RNG stream, NN choices and collision verdicts), same parents, edge
+    lengths, visit counts, node states and returned path."""
+    import ditreeonlineplanner_b200.planners.RRT as rrt_mod
+    import ditreeonlineplanner_b200.planners.base_planner as bp_mod
+    from ditreeonlineplanner_b200 import load_maze
+    g = _Prefixed(golden("tree_scenarios.npz"), k)
+    clock = _FakeClock(0.1)
+    monkeypatch.setattr(rrt_mod, "time", clock)
+    monkeypatch.setattr(bp_mod, "time", clock)
+    smp = _ReplaySampler(g)
+    torch.manual_seed(42)
+    np.random.seed(42)
+    random.seed(42)
+    pl = make_planner(load_maze(str(g["maze"])), g["start"], g["goal"], sampler=smp, time_budget=30, max_iter=300)
+    pl.reset()
+    path, actions = pl.plan()
+    assert smp.i == int(g["n_calls"]) and pl.results["iterations"] == int(g["iterations"])
+    nodes = pl.node_list
+    assert np.array_equal([-1 if n.parent is None else n.parent.index for n in nodes], g["parent"])
+    assert np.array_equal([0 if n.parent_action_seq is None else len(n.parent_action_seq) for n in nodes], g["edge_len"])
+    assert np.array_equal([n.num_visit for n in nodes], g["visits"])
+    assert rel(np.array([n.state for n in nodes]), g["states"]) < 1e-4 and smp.max_obs_err < 1e-4
+    assert path.shape == g["path"].shape and actions.shape == g["actions"].shape
+    assert rel(path, g["path"]) < 1e-4 and rel(actions, g["actions"]) < 1e-6
+
+
 def test_tree_sampler_calls_match_reference(car_meta):
     """Every sampler call the reference made while growing that tree, re-issued to the bf16
     denoiser with the same weights and noise: actions within the 2e-2 tolerance."""

@@ -485,6 +485,76 @@ def gen_tree():
          actions=np.zeros((0, 2), np.float32) if actions is None else actions)
 
 
+def gen_tree_scenarios(time_budget=30):
+    """SURVEY 8c item 10 on EVERY row of experiments/test_scenarios_car.csv: the reference planner at B = 1 under
+    a fake clock (0.1 s per time.time() call, `time_budget` fake seconds) with the small denoiser, seeds as run_scenarios.py:86-90; the tree and
+    the sampler's inputs / outputs per call (no noise: the replay test teacher-forces the actions)."""
+    import csv
+    import planners.RRT as rrt_mod
+    import planners.base_planner as bp_mod
+    dims = [64, 128, 256]
+    sd = denoiser_ref.init_params(seed=21, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims)
+    net = ConditionalUnet1DWithLocalMap(input_dim=2, encoder_name="resnet", embedding_dim=400,
+                                        additional_global_cond_dim=7, local_map_size=20, down_dims=dims)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with open("experiments/test_scenarios_car.csv") as f:
+        rows = list(csv.DictReader(f))
+    out = {"n": np.array(len(rows)), "time_budget": np.array(time_budget)}
+    for k, row in enumerate(rows):
+        smp = DiffusionSampler(net, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2,
+                               obs_history=1, action_history=1, goal_conditioned=True, num_diffusion_iters=1,
+                               local_map_size=20).eval()
+        smp.device = "cpu"
+        calls = []
+        orig_forward = smp.forward
+
+        def recording_forward(obs_seq, prev_actions, goal=None, local_map=None, _orig=orig_forward, _calls=calls):
+            res = _orig(obs_seq, prev_actions, goal=goal, local_map=local_map)
+            _calls.append(dict(obs=np.array(obs_seq, dtype=np.float64)[0, -1], has_prev=prev_actions is not None,
+                               goal=np.array(goal, dtype=np.float64), actions=np.array(res[0][:8], dtype=np.float64)))
+            return res
+        smp.forward = recording_forward
+        maze = load_maze(row["maze_name"])
+        env = car_env.CarEnv(maze_map=maze, collision_checking=False)
+        start_xy = env.cell_rowcol_to_xy(np.array([int(row["start_row"]), int(row["start_col"])]))
+        goal_xy = env.cell_rowcol_to_xy(np.array([int(row["goal_row"]), int(row["goal_col"])]))
+        start = np.array([start_xy[0], start_xy[1], np.deg2rad(float(row["start_deg"])), 0.0, 0.0, 0.0])
+        goal = np.array([goal_xy[0], goal_xy[1], 0.0, 0.0, 0.0, 0.0])
+        torch.manual_seed(42)
+        np.random.seed(42)
+        random.seed(42)
+        clock = _FakeClock(0.1)
+        rrt_mod.time = clock
+        bp_mod.time = clock
+        pl = RRT_Planner(start, goal, env_id="carmaze", environment=env, sampler=smp, prediction_type="actions",
+                         action_horizon=8, local_map_size=20, local_map_scale=0.2, global_map_scale=1.0,
+                         goal_conditioning_bias=0.85, prop_duration=[64], time_budget=time_budget, max_iter=300,
+                         verbose=False)
+        pl.reset()
+        path, actions = pl.plan()
+        nodes = pl.node_list
+        print(f"  {k:2d} {row['scenario_name']:>16s}: {pl.results['iterations']} iterations, {len(nodes)} nodes, "
+              f"{len(calls)} sampler calls, path {'none' if path is None else path.shape}")
+        pre = f"{k}."
+        out[pre + "maze"] = np.array(row["maze_name"])
+        out[pre + "start"], out[pre + "goal"] = start, goal
+        out[pre + "parent"] = np.array([-1 if n.parent is None else nodes.index(n.parent) for n in nodes], np.int32)
+        out[pre + "states"] = np.array([n.state for n in nodes])
+        out[pre + "visits"] = np.array([n.num_visit for n in nodes], np.int32)
+        out[pre + "edge_len"] = np.array([0 if n.parent_action_seq is None else len(n.parent_action_seq) for n in nodes],
+                                         np.int32)
+        out[pre + "iterations"] = np.array(pl.results["iterations"])
+        out[pre + "call_obs"] = np.array([c["obs"] for c in calls])
+        out[pre + "call_has_prev"] = np.array([c["has_prev"] for c in calls])
+        out[pre + "call_actions"] = np.array([c["actions"] for c in calls])
+        out[pre + "call_goal"] = np.array([c["goal"] for c in calls])
+        out[pre + "n_calls"] = np.array(len(calls))
+        out[pre + "path"] = np.zeros((0, 6), np.float32) if path is None else path
+        out[pre + "actions"] = np.zeros((0, 2), np.float32) if actions is None else actions
+    save("tree_scenarios.npz", **out)
+
+
 def gen_probmap():
     """run_type >= 2 sampler: SciPy EDT prior on every maze, gaussian_map + combine_log_blend for seeded
     (robot, goal) pairs on the 20 x 20 mazes, and np.random.choice draws with the uniform variates that
@@ -535,10 +605,10 @@ def gen_probmap():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["data", "schedule", "local_map", "collide_car", "collide_ant", "bicycle", "propagate",
-                             "cond", "denoiser", "lidar", "probe", "tree", "probmap"]
+                             "cond", "denoiser", "lidar", "probe", "tree", "tree_scenarios", "probmap"]
     fns = dict(data=gen_data_fixtures, schedule=gen_schedule, local_map=gen_local_map, collide_car=gen_collide_car,
                collide_ant=gen_collide_ant, bicycle=gen_bicycle, propagate=gen_propagate, cond=gen_cond,
-               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, tree=gen_tree, probmap=gen_probmap)
+               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, tree=gen_tree, tree_scenarios=gen_tree_scenarios, probmap=gen_probmap)
     for w in which:
         print(f"[{w}]")
         fns[w]()

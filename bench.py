@@ -270,7 +270,7 @@ def main():
         from ditreeonlineplanner_b200 import scenarios as sc
         from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
         invalidate_staged_map()
-        suite_kw = {"batch_size": 256, "iteration_cap": 256 * 8 * 2}
+        suite_kw = {"batch_size": 256, "iteration_cap": 256 * 8 * 2}  # 8 passes per slot group = one full 64-step edge per slot
         # untimed warm-up unit: builds the planner's second device context, captures its graphs
         sc.run_car_unit(sc.load_scenarios("test_scenarios_car")[0], 0, 0, sampler, 1e9, suite_kw)
         barrier()
@@ -287,7 +287,8 @@ def main():
                          "4096 chunk expansions (the reference's iteration count) or goal, K=1 (the reference's "
                          "planning_diffusion_iters), large denoiser",
                  "mean_tree_nodes": float(np.mean(rows_t[:, 6][rows_t[:, 6] > 0])) if (rows_t[:, 6] > 0).any() else 0.0,
-                 "gather": "one all_gather of [units/rank, 13] fp32 rows"}
+                 "schedule": "ranks pull units from one shared counter (process-group store), heaviest maps first",
+                 "gather": "one all_gather of [units, 13] fp32 rows"}
         ctx.set_map(grid)
         invalidate_staged_map()
 

@@ -21,11 +21,15 @@ ROW_FIELDS = ["iteration", "success", "runtime", "trajectory_length", "trajector
               "num_states_in_tree", "num_RRT_iterations", "ctrl_effort_max", "ctrl_effort_mean", "ctrl_effort_std"]
 
 
-def all_units(n_scenarios, total_runs, weights=None):
-    """Every (scenario, run) unit, heaviest scenario first (weights default to equal)."""
+def all_units(n_scenarios, total_runs, weights=None, by_weight=False):
+    """Every (scenario, run) unit, heaviest scenario first (weights default to equal).  Run-major by default
+    (every rank of a round-robin deal gets the same mix); `by_weight` lists ALL runs of the heaviest scenario
+    first -- the longest-processing-time order a shared work queue wants."""
     order = list(range(n_scenarios))
     if weights is not None:
         order.sort(key=lambda i: -weights[i])
+    if by_weight:
+        return [(s, r) for s in order for r in range(total_runs)]
     return [(s, r) for r in range(total_runs) for s in order]
 
 
@@ -83,10 +87,31 @@ def run_car_unit(row, scenario_idx, run_idx, sampler, time_budget, planner_kwarg
     return result_row(run_idx, path, actions, planner.results, time.time() - t0)
 
 
-def gather_rows(local_units, local_rows, n_units_total, device, world):
+_QUEUE_CALLS = 0
+
+
+def queued_units(units, world):
+    """Dynamic deal: ranks pull the next unit index from one shared counter in the process group's key-value
+    store (control plane only -- an integer per unit; no tensor leaves a GPU).  A rank that drew short units
+    takes more of them, so the suite ends when the LAST unit ends rather than when the unluckiest static
+    share does.  Results do not depend on who ran a unit: every unit is seeded from (scenario, run)."""
+    global _QUEUE_CALLS
+    import torch.distributed as dist
+    from torch.distributed.distributed_c10d import _get_default_store
+    _QUEUE_CALLS += 1  # run_suite is collective: every rank is at the same call number
+    store, key = _get_default_store(), f"ditree/suite_queue/{_QUEUE_CALLS}"
+    while True:
+        i = store.add(key, 1) - 1
+        if i >= len(units):
+            return
+        yield units[i]
+
+
+def gather_rows(local_units, local_rows, n_units_total, device, world, per_rank=None):
     """all_gather the fixed-size result rows; returns {(scenario, run): row} on every rank."""
     import torch.distributed as dist
-    per_rank = (n_units_total + world - 1) // world
+    if per_rank is None:
+        per_rank = (n_units_total + world - 1) // world
     buf = torch.full((per_rank, 2 + len(ROW_FIELDS)), float("nan"), dtype=torch.float32, device=device)
     for i, ((s, r), row) in enumerate(zip(local_units, local_rows)):
         buf[i, 0], buf[i, 1] = s, r
@@ -105,14 +130,24 @@ def gather_rows(local_units, local_rows, n_units_total, device, world):
 
 
 def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car", rank=0, world=1, device="cuda",
-              planner_kwargs=None, unit_fn=run_car_unit):
-    """Run this rank's share of the suite and gather everybody's rows.  -> (table, seconds)."""
+              planner_kwargs=None, unit_fn=run_car_unit, schedule="queue"):
+    """Run this rank's share of the suite and gather everybody's rows.  -> (table, seconds).
+    schedule: "queue" (default for world > 1) -- ranks pull units from a shared counter, heaviest maps first;
+    "static" -- the round-robin deal of shard_units."""
     rows = load_scenarios(kind)
     weights = [int(np.prod(load_maze(r["maze_name"]).shape)) for r in rows]
-    mine = shard_units(len(rows), total_runs, rank, world, weights)
+    n_total = len(rows) * total_runs
     t0 = time.time()
-    local = [unit_fn(rows[s], s, r, sampler, time_budget, planner_kwargs) for s, r in mine]
-    table = gather_rows(mine, local, len(rows) * total_runs, device, world)
+    if world > 1 and schedule == "queue":
+        mine, local = [], []
+        for s, r in queued_units(all_units(len(rows), total_runs, weights, by_weight=True), world):
+            mine.append((s, r))
+            local.append(unit_fn(rows[s], s, r, sampler, time_budget, planner_kwargs))
+        table = gather_rows(mine, local, n_total, device, world, per_rank=n_total)
+    else:
+        mine = shard_units(len(rows), total_runs, rank, world, weights)
+        local = [unit_fn(rows[s], s, r, sampler, time_budget, planner_kwargs) for s, r in mine]
+        table = gather_rows(mine, local, n_total, device, world)
     return table, time.time() - t0
 
 

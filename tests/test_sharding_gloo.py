@@ -23,12 +23,26 @@ def _fake_unit(row, s, r, sampler, time_budget, planner_kwargs):
     return [r + 1, s % 2, 0.1, float(np.random.rand()), 0.0, 1.0, 10 + s, 100 + r, 1.0, 0.5, 0.1]
 
 
+_RAN = []
+
+
+def _recording_unit(row, s, r, sampler, time_budget, planner_kwargs):
+    import time
+    _RAN.append((s, r))
+    time.sleep(0.002 * (1 + s % 3))  # uneven units: the queue must still hand out each exactly once
+    return _fake_unit(row, s, r, sampler, time_budget, planner_kwargs)
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    table, _ = sc.run_suite(None, total_runs=3, rank=rank, world=world, device="cpu", unit_fn=_fake_unit)
-    q.put((rank, sorted(table.items())))
+    table, _ = sc.run_suite(None, total_runs=3, rank=rank, world=world, device="cpu", unit_fn=_recording_unit)
+    queued = list(_RAN)
+    static, _ = sc.run_suite(None, total_runs=3, rank=rank, world=world, device="cpu", unit_fn=_fake_unit,
+                             schedule="static")
+    again, _ = sc.run_suite(None, total_runs=2, rank=rank, world=world, device="cpu", unit_fn=_fake_unit)  # fresh counter
+    q.put((rank, sorted(table.items()), sorted(static.items()), queued, len(again)))
     dist.destroy_process_group()
 
 
@@ -58,10 +72,15 @@ def test_gather_world2_matches_world1():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, items in got:
-        assert dict(items).keys() == single.keys()
-        for k, v in items:
-            np.testing.assert_allclose(v, single[k], rtol=1e-6)
+    for rank, items, static_items, queued, n_again in got:
+        assert n_again == 30
+        for table in (items, static_items):  # shared-queue deal and round-robin deal: the same rows on every rank
+            assert dict(table).keys() == single.keys()
+            for k, v in table:
+                np.testing.assert_allclose(v, single[k], rtol=1e-6)
+    ran = [u for g in got for u in g[3]]
+    assert sorted(ran) == sorted(single.keys()) and len(set(ran)) == 45  # every unit ran on exactly one rank
+    assert all(len(g[3]) > 0 for g in got)
 
 
 def test_result_row_schema():

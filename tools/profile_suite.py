@@ -12,7 +12,7 @@ ctx = get_context(0)
 sd = random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=UNET_DIMS["large"])
 sampler = DiffusionSampler(sd, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2, obs_history=1,
                            action_history=1, goal_conditioned=True, num_diffusion_iters=1, local_map_size=20, max_batch=4096).eval()
-kw = {"batch_size": int(os.environ.get("BATCH", "256")), "iteration_cap": int(os.environ.get("BATCH", "256")) * 8 * 2}
+kw = {"batch_size": int(os.environ.get("BATCH", "256")), "iteration_cap": int(os.environ.get("ITER_CAP", "4096"))}
 sc.run_suite(sampler, total_runs=1, time_budget=1e9, planner_kwargs=kw)  # warm
 torch.cuda.synchronize()
 pr = cProfile.Profile()

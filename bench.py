@@ -286,6 +286,7 @@ def main():
                  "unit": "one (scenario, run) of test_scenarios_car: batched RRT with continuous slot refill, 2 x 256 slots on two streams, "
                          "4096 chunk expansions (the reference's iteration count) or goal, K=1 (the reference's "
                          "planning_diffusion_iters), large denoiser",
+                 "unit_seconds_sum": float(rows_t[:, 2].sum()),
                  "mean_tree_nodes": float(np.mean(rows_t[:, 6][rows_t[:, 6] > 0])) if (rows_t[:, 6] > 0).any() else 0.0,
                  "schedule": "ranks pull units from one shared counter (process-group store), heaviest maps first",
                  "gather": "one all_gather of [units, 13] fp32 rows"}

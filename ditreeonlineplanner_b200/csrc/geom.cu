@@ -24,6 +24,66 @@ k_collide_car(MapView m, QMapView q, const float* __restrict__ x, const float* _
   }
 }
 
+// Four consecutive states per thread: the four guard-banded fast tests are straight-line code the scheduler
+// interleaves (the single-state kernel is latency-bound at half occupancy), the rare exact decisions are
+// taken afterwards behind one branch, and the four flags leave as one 32-bit store.  Needs the quadrant
+// table and a 4-byte aligned flag array; states B - B % 4 .. B - 1 take the single-state path.
+// (Measured: 0.100 -> 0.079 ms for 2^24 states; a lane-strided assignment -- 32 states apart, byte stores --
+// is slower, 0.092 ms: the kernel is issue-bound, ~160 instructions per state, not load-coalescing bound.)
+#ifndef COLL4_MINB
+#define COLL4_MINB 3  // resident blocks per SM the register allocation is held to (80 registers, no spills)
+#endif
+__global__ void __launch_bounds__(GEOM_THREADS, COLL4_MINB)
+k_collide_car4(MapView m, QMapView q, const float* __restrict__ x, const float* __restrict__ y,
+               const float* __restrict__ th, int64_t stride, int64_t B, uint8_t* __restrict__ out,
+               int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_map[];
+  __shared__ uint64_t bar;
+  uint32_t* s_q = reinterpret_cast<uint32_t*>(s_map + m.bytes);
+  dt_stage_maps(s_map, s_q, &bar, m, q);
+  const uint32_t q_addr = dt_qmap_addr(s_q, q);
+  const int64_t quads = B >> 2;
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, total = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = gtid; t < quads; t += total) {
+    float xs[4], ys[4], ts[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t o = (4 * t + j) * stride;
+      xs[j] = x[o];
+      ys[j] = y[o];
+      ts[j] = th[o];
+    }
+    uint32_t flags = 0, rare = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool th_ok = fabsf(ts[j]) <= DT_SC_MAX;  // false for NaN / huge headings: the exact code decides,
+      float sn, cs;                                  // the fast test runs on heading 0 (its table address must stay valid)
+      dt_sincos_mufu(th_ok ? ts[j] : 0.f, sn, cs);
+      bool amb;
+      const bool hit = dt_car_fast(q_addr, q, xs[j], ys[j], sn, cs, amb);
+      flags |= (hit ? 1u : 0u) << (8 * j);
+      rare |= ((amb || !th_ok) ? 1u : 0u) << j;
+    }
+    if (rare) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((rare >> j) & 1u) {
+          const int r = dt_car_test_exact(s_map, m.rows, m.cols, xs[j], ys[j], ts[j]);
+          if (r & 4) atomicMin(status, DT_E_INDEX);
+          flags = (flags & ~(0xFFu << (8 * j))) | ((uint32_t)(r & 1) << (8 * j));
+        }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(out + 4 * t) = flags;
+  }
+  const int64_t i = 4 * quads + gtid;
+  if (i < B) {
+    const int r = dt_car_any(s_map, q_addr, q, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
+    if (r & 4) atomicMin(status, DT_E_INDEX);
+    out[i] = (uint8_t)(r & 1);
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // is_colliding_parallel  (common/map_utils.py:221-329), two passes for the batch early return
 // -------------------------------------------------------------------------------------------
@@ -385,8 +445,13 @@ extern "C" int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const
     q.g = nullptr;
     q.bytes = 0;
   }
-  k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
-      m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+  if (q.g && B >= 4 && (reinterpret_cast<uintptr_t>(flags_out) & 3u) == 0) {
+    k_collide_car4<<<grid_for((B + 3) / 4, GEOM_THREADS, ctx, COLL4_MINB), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
+        m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+  } else {
+    k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
+        m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+  }
   DT_LAUNCH_CHECK("k_collide_car");
   return DT_OK;
 }

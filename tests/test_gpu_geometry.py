@@ -52,6 +52,32 @@ def test_collide_car_2m_vs_oracle(ctx, mazes, maze):
     assert np.array_equal(got, want), f"{np.sum(got != want)} flags differ"
 
 
+def test_collide_car_ragged_sizes_and_special_values(ctx, mazes):
+    """The four-states-per-thread kernel and its single-state tail: batch sizes around the multiples of four,
+    shifted views (the flag array stays aligned, the states do not), non-finite positions, NaN / huge headings
+    (must agree with the single-state kernel, which takes the exact code for them)."""
+    rng = np.random.default_rng(3)
+    for maze in ("boxes", "random_huge", "narrow_short"):
+        grid = mazes[maze]
+        R, C = grid.shape
+        ctx.set_map(grid)
+        for n in (1, 3, 4, 5, 7, 1027, 100_003):
+            st = np.stack([rng.uniform(-C / 2 - 1, C / 2 + 1, n), rng.uniform(-R / 2 - 1, R / 2 + 1, n),
+                           rng.uniform(-7, 7, n)], 1).astype(np.float32)
+            special = []
+            if n > 100:
+                st[7], st[8], st[9], st[10] = [np.nan, 0, 0], [0, 0, np.nan], [0.3, 0.2, 1e6], [np.inf, 0, 0]
+                special = [7, 8, 9, 10]
+            d = dev(st)
+            got = ctx.collide_car(d).cpu().numpy().astype(bool)
+            for i in special:
+                assert got[i] == bool(ctx.collide_car(d[i:i + 1]).item()), (maze, n, i)
+            keep = np.setdiff1d(np.arange(n), special)
+            assert np.array_equal(got[keep], orc.collide_car_batch(st[keep].astype(np.float64), grid)), (maze, n)
+            if n > 1:
+                assert np.array_equal(ctx.collide_car(d[1:]).cpu().numpy().astype(bool), got[1:])
+
+
 def test_collide_points_semantics(ctx, mazes):
     g = golden("collide_car.npz")
     ctx.set_map(mazes["boxes"])

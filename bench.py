@@ -181,8 +181,11 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "note": "reference CPU path = NumPy/torch-CPU oracle port; the "
-                           "Python reference itself cannot travel to the GPU box"},
+                "config": {"workload": workload, "candidates_per_gpu": args.batch, "ode_steps": args.ode_steps,
+                           "rollout_steps": args.rollout,
+                           "weights": "random-init, reference architecture (184 M parameters)",
+                           "note": "reference CPU path = NumPy/torch-CPU oracle port; the Python reference itself "
+                                   "cannot travel to the GPU box; each step is the bounded sample named in cpu_baseline"},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)

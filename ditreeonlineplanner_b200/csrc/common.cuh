@@ -1,6 +1,7 @@
 // common.cuh -- context, error plumbing and the shared-memory map staging used by every kernel.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>

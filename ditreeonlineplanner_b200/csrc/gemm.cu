@@ -1091,15 +1091,26 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);
 
 // -> 0 = not applicable (caller continues with the fused path), 1 = done, negative = error
 static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
-  if (!ctx->splitk_on || ctx->prof_on || g.ksplit > 1 || g.T > 64 || g.B * g.T > 128 || 128 % g.T != 0) return 0;
+  if (!ctx->splitk_on || ctx->prof_on || g.ksplit > 1) return 0;
+  // two shapes qualify: (a) whole samples inside ONE 128-row tile (the U-Net at a few candidates), and
+  // (b) a flat [rows, N] problem -- one "sample", plain epilogue -- with a handful of 128-row tiles and a
+  // long K (the encoder's last stages at planner batch sizes: 256 x 512 x 4608 is four tiles on 148 SMs)
+  const bool few_rows = g.T <= 64 && g.B * g.T <= 128 && 128 % g.T == 0;
+  const bool flat = !few_rows && g.epi == EPI_PLAIN && g.B == 1 && g.out_t_stride == 1 && g.T <= 8192;
+  if (!few_rows && !flat) return 0;
   long long nkb = 0;
   for (int s = 0; s < g.nseg; ++s) nkb += g.seg[s].nblk;
   const int rows = (int)(g.B * g.T);
   const int bn = (g.N % 256 == 0) ? 256 : ((g.N % 128 == 0) ? 128 : 64);
-  const int n_tiles = g.N / bn;
-  if (nkb < 8 || n_tiles * 4 > ctx->sm_count) return 0;
+  const int n_tiles = (g.N / bn) * (flat ? (rows + BM - 1) / BM : 1);
+  if (nkb < (flat ? 64 : 8) || n_tiles * 4 > ctx->sm_count) return 0;  // flat: measured win only from K = 4096 up (35 -> 27 us)
   int ksplit = ctx->sm_count / n_tiles;              // one work item per SM
-  if (ksplit > nkb / 2) ksplit = (int)(nkb / 2);     // at least two K blocks per item
+  if (flat) {                                        // several tiles: the reduction reads ksplit x the output,
+    if (ksplit > nkb / 4) ksplit = (int)(nkb / 4);   // keep the slices long and few
+    if (ksplit > 16) ksplit = 16;
+  } else if (ksplit > nkb / 2) {
+    ksplit = (int)(nkb / 2);                         // at least two K blocks per item
+  }
   if (ksplit < 2) return 0;
   const int per = (int)((nkb + ksplit - 1) / ksplit);
   ksplit = (int)((nkb + per - 1) / per);             // no empty slice
@@ -1125,14 +1136,24 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   e.bias = g.bias; e.gamma = g.gamma; e.beta = g.beta; e.film = g.film; e.film_ld = g.film_ld; e.film_t = g.film_t;
   e.resid = g.resid; e.ld_res = g.ld_res; e.out_bf16 = g.out_bf16; e.out_f32 = g.out_f32;
   e.ldc = g.ldc; e.out_b_stride = g.out_b_stride; e.out_t_stride = g.out_t_stride; e.out_off = g.out_off;
-  // cluster size: up to 8 CTAs per window, T / CS whole rows each
-  int cs = 8;
-  while (cs > 1 && g.T % cs != 0) cs >>= 1;
+  int64_t windows_b = g.B;
+  int cs = 8;  // cluster size: up to 8 CTAs per window, T / CS whole rows each
+  if (flat) {
+    // rows are independent (no GroupNorm): re-cut the one sample into windows of up to 16 consecutive rows,
+    // one CTA each (1024 elements: four per thread)
+    int t2 = 16;
+    while (rows % t2 != 0) t2 >>= 1;
+    e.T = t2;
+    e.out_b_stride = t2;  // out_t_stride == 1: row = b2 * t2 + t
+    windows_b = rows / t2;
+    cs = 1;
+  }
+  while (cs > 1 && e.T % cs != 0) cs >>= 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3((unsigned)(g.B * (g.N / e.gw) * cs));
+  cfg.gridDim = dim3((unsigned)(windows_b * (g.N / e.gw) * cs));
   cfg.blockDim = dim3(SPLITK_EPI_THREADS);
-  cfg.dynamicSmemBytes = (size_t)(g.T / cs) * e.gw * sizeof(float);
+  cfg.dynamicSmemBytes = (size_t)(e.T / cs) * e.gw * sizeof(float);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

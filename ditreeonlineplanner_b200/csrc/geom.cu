@@ -186,7 +186,7 @@ __device__ __forceinline__ int local_map_cell_exact(const MapView& m, double cs,
 template <typename OutT>
 __global__ void __launch_bounds__(GEOM_THREADS)
 k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
-            int64_t stride, int64_t B, int N, Axis ax, OutT* __restrict__ out) {
+            int64_t stride, int64_t B, int N, Axis ax, int pair, OutT* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
   dt_stage_map(s_map, &bar, m);
@@ -211,48 +211,88 @@ k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y,
     // non-finite poses or an eps that swallows a cell: everything through the exact code
     const bool fast_ok = eps < 0.25f;
     OutT* o = out + b * (int64_t)(N * N);
-    int i = lane / N, j = lane - i * N;  // out[i, j] uses ys[i], xs[j]; advanced incrementally (no division)
-    for (int p = lane; p < N * N; p += 32) {
-      int cell;
-      bool exact = !fast_ok;
-      if (fast_ok) {
-        // axis values arithmetically (an indexed constant-bank load per point stalls the FMA chain): within
-        // 1 ulp of float(linspace), covered by eps
-        const float xl = fmaf((float)j, ax.stepf, ax.startf), yl = fmaf((float)i, ax.stepf, ax.startf);
-        const float xg = fmaf(csf, xl, fmaf(-snf, yl, pxf));
-        const float yg = fmaf(snf, xl, fmaf(csf, yl, pyf));
-        // grid coordinates shifted by +2 and clamped half a cell outside the map: floor by a round-down add
-        // of 2^23 (the integer lands in the mantissa; no conversion instructions), in-cell offset exact
-        const float M23 = 8388608.0f;
-        const float u = fminf(fmaxf(fmaf(-yg, inv_s, cy2), 1.5f), rmax + 2.5f);
-        const float w = fminf(fmaxf(fmaf(xg, inv_s, cx2), 1.5f), cmax + 2.5f);
-        const float tu = __fadd_rd(u, M23), tw = __fadd_rd(w, M23);
-        const float du = u - (tu - M23), dw = w - (tw - M23);
-        // any cell border closer than eps sends the point to the float64 code
-        exact = fminf(fminf(du, 1.0f - du), fminf(dw, 1.0f - dw)) < eps;
-        const int yi = min(max(__float_as_int(tu) - (0x4B000000 + 2), 0), m.rows - 1);
-        const int xi = min(max(__float_as_int(tw) - (0x4B000000 + 2), 0), m.cols - 1);
-        cell = yi * m.cols + xi;
+    // fast-path cell of point (i, j); `exact` is set when the float64 code must decide it
+    auto fast_cell = [&](int i, int j, bool& exact) -> int {
+      // axis values arithmetically (an indexed constant-bank load per point stalls the FMA chain): within
+      // 1 ulp of float(linspace), covered by eps
+      const float xl = fmaf((float)j, ax.stepf, ax.startf), yl = fmaf((float)i, ax.stepf, ax.startf);
+      const float xg = fmaf(csf, xl, fmaf(-snf, yl, pxf));
+      const float yg = fmaf(snf, xl, fmaf(csf, yl, pyf));
+      // grid coordinates shifted by +2 and clamped half a cell outside the map: floor by a round-down add
+      // of 2^23 (the integer lands in the mantissa; no conversion instructions), in-cell offset exact
+      const float M23 = 8388608.0f;
+      const float u = fminf(fmaxf(fmaf(-yg, inv_s, cy2), 1.5f), rmax + 2.5f);
+      const float w = fminf(fmaxf(fmaf(xg, inv_s, cx2), 1.5f), cmax + 2.5f);
+      const float tu = __fadd_rd(u, M23), tw = __fadd_rd(w, M23);
+      const float du = u - (tu - M23), dw = w - (tw - M23);
+      // any cell border closer than eps sends the point to the float64 code
+      exact = fminf(fminf(du, 1.0f - du), fminf(dw, 1.0f - dw)) < eps;
+      const int yi = min(max(__float_as_int(tu) - (0x4B000000 + 2), 0), m.rows - 1);
+      const int xi = min(max(__float_as_int(tw) - (0x4B000000 + 2), 0), m.cols - 1);
+      return yi * m.cols + xi;
+    };
+    auto exact_cell = [&](int i, int j) -> int {
+      if (!have_exact_trig) {
+        sincos((double)thf, &sn, &cs);
+        have_exact_trig = true;
       }
-      if (exact) {
-        if (!have_exact_trig) {
-          sincos((double)thf, &sn, &cs);
-          have_exact_trig = true;
-        }
-        cell = local_map_cell_exact(m, cs, sn, px, py, cx, cy, ax.v[j], ax.v[i]);
-      }
+      return local_map_cell_exact(m, cs, sn, px, py, cx, cy, ax.v[j], ax.v[i]);
+    };
+    auto occupancy = [&](int cell) -> float {
       uint32_t occ_u;
       asm("ld.shared.u8 %0, [%1];" : "=r"(occ_u) : "r"(s_map_u + (uint32_t)cell));
-      const float occ = (float)occ_u;
-      if (sizeof(OutT) == 4) {
-        o[p] = (OutT)occ;
-      } else {
-        o[p] = (OutT)(occ * 2.0f - 1.0f);  // sampler's rescale to [-1, 1] (fm_policy.py:152)
+      return (float)occ_u;
+    };
+    const int NN = N * N;
+    if (pair) {
+      // two neighbouring points per lane and step: two independent chains in flight, one packed store
+      int i = (2 * lane) / N, j = 2 * lane - i * N;  // advanced incrementally (no division)
+      for (int p = 2 * lane; p < NN; p += 64) {
+        int i1 = i, j1 = j + 1;
+        if (j1 == N) {
+          j1 = 0;
+          ++i1;
+        }
+        int c0 = 0, c1 = 0;
+        bool e0 = !fast_ok, e1 = !fast_ok;
+        if (fast_ok) {
+          c0 = fast_cell(i, j, e0);
+          c1 = fast_cell(i1, j1, e1);
+        }
+        if (e0 | e1) {
+          if (e0) c0 = exact_cell(i, j);
+          if (e1) c1 = exact_cell(i1, j1);
+        }
+        const float v0 = occupancy(c0), v1 = occupancy(c1);
+        if (sizeof(OutT) == 4) {
+          *reinterpret_cast<float2*>(o + p) = make_float2(v0, v1);
+        } else {  // sampler's rescale to [-1, 1] (fm_policy.py:152)
+          *reinterpret_cast<__nv_bfloat162*>(o + p) = __floats2bfloat162_rn(v0 * 2.0f - 1.0f, v1 * 2.0f - 1.0f);
+        }
+        j += 64;
+        while (j >= N) {
+          j -= N;
+          ++i;
+        }
       }
-      j += 32;
-      while (j >= N) {
-        j -= N;
-        ++i;
+    } else {
+      int i = lane / N, j = lane - i * N;  // out[i, j] uses ys[i], xs[j]
+      for (int p = lane; p < NN; p += 32) {
+        bool exact = !fast_ok;
+        int cell = 0;
+        if (fast_ok) cell = fast_cell(i, j, exact);
+        if (exact) cell = exact_cell(i, j);
+        const float occ = occupancy(cell);
+        if (sizeof(OutT) == 4) {
+          o[p] = (OutT)occ;
+        } else {
+          o[p] = (OutT)(occ * 2.0f - 1.0f);
+        }
+        j += 32;
+        while (j >= N) {
+          j -= N;
+          ++i;
+        }
       }
     }
   }
@@ -516,10 +556,14 @@ extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const f
   int64_t blocks = (B + warps - 1) / warps;
   if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
   cudaStream_t st = (cudaStream_t)stream;
+  // paired points (packed 8- / 4-byte stores) need an even point count per pose and an aligned output
+  const int even = ((N * N) & 1) == 0;
   if (out_dtype == DT_F32) {
-    k_local_map<float><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, (float*)out);
+    const int pair = even && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    k_local_map<float><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair, (float*)out);
   } else if (out_dtype == DT_BF16) {
-    k_local_map<__nv_bfloat16><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax,
+    const int pair = even && (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+    k_local_map<__nv_bfloat16><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair,
                                                                           (__nv_bfloat16*)out);
   } else {
     return dt_fail(ctx, DT_E_ARG, "dt_local_map: unknown out_dtype");

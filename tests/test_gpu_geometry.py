@@ -149,6 +149,23 @@ def test_local_map_100k_vs_oracle(ctx, mazes):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n_side", [2, 5, 15, 32])
+def test_local_map_other_sizes(ctx, mazes, n_side):
+    """Odd point counts take the one-point-per-lane path, even ones the paired path; both output types."""
+    grid = mazes["random_huge"]
+    ctx.set_map(grid)
+    rng = np.random.default_rng(n_side)
+    n = 3000
+    R, C = grid.shape
+    pose = np.stack([rng.uniform(-C / 2 - 1, C / 2 + 1, n), rng.uniform(-R / 2 - 1, R / 2 + 1, n),
+                     rng.uniform(-7, 7, n)], 1).astype(np.float32)
+    p64 = pose.astype(np.float64)
+    want = orc.local_map(grid, p64[:, 0], p64[:, 1], p64[:, 2], n_side, 0.3, 1.0, (C / 2, R / 2))
+    assert np.array_equal(ctx.local_map(dev(pose), n_side, 0.3).cpu().numpy(), want)
+    signed = ctx.local_map(dev(pose), n_side, 0.3, bf16_signed=True).float().cpu().numpy()
+    assert np.array_equal(signed, want.astype(np.float32) * 2 - 1)
+
+
 # ---- dynamics ------------------------------------------------------------------------------
 def rel_err(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)

@@ -24,7 +24,9 @@
 
 #define BM 128
 #define BK 64
+#ifndef EPI_SPLIT
 #define EPI_SPLIT 2                      // epilogue warps per TMEM lane quarter (column split)
+#endif
 #define GEMM_THREADS (64 + 128 * EPI_SPLIT)
 #define SPIN_LIMIT (1u << 24)
 

@@ -312,7 +312,12 @@ class RRT_Planner(BasePlanner):
             g = Group()
             g.ctx = group_ctx[gi]
             g.stream = torch.cuda.Stream(device=dev)
-            g.h_in = torch.empty((B, W_IN), dtype=torch.float32).pin_memory()
+            # one pinned block, three contiguous parts (states | previous actions | goals): one H2D copy per
+            # pass and the device views need no gather kernels
+            g.h_in = torch.empty(B * W_IN, dtype=torch.float32).pin_memory()
+            g.hin_s = g.h_in[:B * 6].view(B, 6).numpy()
+            g.hin_p = g.h_in[B * 6:B * (6 + A)].view(B, A).numpy()
+            g.hin_g = g.h_in[B * (6 + A):].view(B, 2).numpy()
             g.h_out = torch.empty((B, W_OUT), dtype=torch.float32).pin_memory()
             g.parent = [None] * B              # Node the slot's edge grows from
             g.chunk = np.zeros(B, dtype=np.int64)
@@ -331,24 +336,25 @@ class RRT_Planner(BasePlanner):
                 return
             samples, goals = self._sample_batch(k)
             parents = self.nearest_node_batch(samples)
-            hin = g.h_in.numpy()
+            hs, hp = g.hin_s, g.hin_p
             for j, b in enumerate(slots):
                 p = parents[j]
                 g.parent[b] = p
                 g.n_chunks[b] = max(1, sched[min(max(p.num_visit, 0), len(sched) - 1)] // h)
                 p.num_visit += 1
                 g.chunk[b] = 0
-                hin[b, :6] = p.state
-                hin[b, 6:6 + A] = mean_np if p.parent_action_seq is None or len(p.parent_action_seq) == 0 \
+                hs[b] = p.state
+                hp[b] = mean_np if p.parent_action_seq is None or len(p.parent_action_seq) == 0 \
                     else p.parent_action_seq[-1]
-            hin[slots, 6 + A:] = goals
+            g.hin_g[slots] = goals
 
         def launch(g):
             c = g.ctx
             g.stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(g.stream):
                 d_in = g.h_in.to(dev, non_blocking=True)
-                states, prev, goals_d = d_in[:, :6].contiguous(), d_in[:, 6:6 + A].contiguous(), d_in[:, 6 + A:].contiguous()
+                states, prev = d_in[:B * 6].view(B, 6), d_in[B * 6:B * (6 + A)].view(B, A)
+                goals_d = d_in[B * (6 + A):].view(B, 2)
                 lm = c.local_map(states, n_map, self.local_map_scale, bf16_signed=True)
                 cond = c.build_cond_car(states, prev, goals_d, smp.metadata, float(n_map))
                 noise = torch.randn((B, smp.pred_horizon, A), device=dev)
@@ -366,7 +372,6 @@ class RRT_Planner(BasePlanner):
             g.event.synchronize()
             g.in_flight = False
             out = g.h_out.numpy().astype(np.float64)
-            hin = g.h_in.numpy()
             traj = out[:, :h * 6].reshape(B, h, 6)
             acts = out[:, h * 6:h * 6 + h * A].reshape(B, h, A)
             fin = out[:, h * 6 + h * A:h * 6 + h * A + 6]
@@ -377,7 +382,7 @@ class RRT_Planner(BasePlanner):
             steps = np.where(done >= 0, done + 1, h)
             ok_slots = np.nonzero(~coll)[0]
             ck = g.chunk[ok_slots]
-            g.hist_s0[ok_slots, ck] = hin[ok_slots, :6]
+            g.hist_s0[ok_slots, ck] = g.hin_s[ok_slots]
             g.hist_a[ok_slots, ck] = acts[ok_slots]
             g.hist_t[ok_slots, ck] = traj[ok_slots]
             g.chunk[ok_slots] += 1
@@ -393,8 +398,8 @@ class RRT_Planner(BasePlanner):
                 new_nodes.append(node)
                 if done[b] >= 0 and goal_node is None:
                     goal_node = node
-            hin[goes_on, :6] = fin[goes_on]        # the edge goes on from the state it reached
-            hin[goes_on, 6:6 + A] = acts[goes_on, h - 1]
+            g.hin_s[goes_on] = fin[goes_on]        # the edge goes on from the state it reached
+            g.hin_p[goes_on] = acts[goes_on, h - 1]
             free = np.nonzero(coll | ends)[0].tolist()
             self._insert_many(new_nodes)
             if self.run_type == 0:

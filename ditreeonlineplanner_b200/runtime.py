@@ -47,7 +47,19 @@ class Context:
             pass
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # raw handle of torch's current stream on this device (the C call behind torch.cuda.current_stream,
+        # without building a Stream object: this runs five times per planner pass)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))
+
+    def _norm_vec(self, meta):
+        """[obs mean | obs std | action mean | action std] float64, built once per metadata dict."""
+        cache = self.__dict__.setdefault("_norm_cache", {})
+        hit = cache.get(id(meta))
+        if hit is None or hit[0] is not meta:
+            vec = np.concatenate([meta["Observations_mean"], meta["Observations_std"], meta["Actions_mean"],
+                                  meta["Actions_std"]]).astype(np.float64)
+            hit = cache[id(meta)] = (meta, vec)
+        return hit[1]
 
     def _check(self, rc):
         if rc != 0:
@@ -213,8 +225,7 @@ class Context:
         prev = None if prev_action is None else self._f32(prev_action).contiguous()
         g = self._f32(goal).contiguous()
         gstride = 0 if g.dim() == 1 else 2
-        norm = np.concatenate([meta["Observations_mean"], meta["Observations_std"], meta["Actions_mean"],
-                               meta["Actions_std"]]).astype(np.float64)
+        norm = self._norm_vec(meta)
         out = torch.empty((B, 7), dtype=torch.float32, device=self.device)
         self._check(self.lib.dt_build_cond_car(self.h, _ptr(st), 6, 1, _ptr(prev), _ptr(g), gstride, B,
                                                norm.ctypes.data_as(C.c_void_p), float(map_size), _ptr(out),
@@ -230,8 +241,7 @@ class Context:
         prev = None if prev_action is None else self._f32(prev_action).contiguous()
         g = self._f32(goal).contiguous()
         gstride = 0 if g.dim() == 1 else 2
-        norm = np.concatenate([meta["Observations_mean"], meta["Observations_std"], meta["Actions_mean"],
-                               meta["Actions_std"]]).astype(np.float64)
+        norm = self._norm_vec(meta)
         out = torch.empty((B, obs_history * 29 + 10), dtype=torch.float32, device=self.device)
         self._check(self.lib.dt_build_cond_ant(self.h, _ptr(o), h, obs_history, _ptr(prev), _ptr(g), gstride, B,
                                                norm.ctypes.data_as(C.c_void_p), float(map_size), _ptr(out),

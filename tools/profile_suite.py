@@ -8,6 +8,13 @@ from ditreeonlineplanner_b200 import get_context, scenarios as sc
 from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler
 from ditreeonlineplanner_b200.weights import UNET_DIMS, random_init
 
+if os.environ.get("OLD_RRT"):  # A/B: load a saved copy of the planner module in place of the package's
+    import importlib.util
+    import ditreeonlineplanner_b200.planners  # noqa: F401
+    spec = importlib.util.spec_from_file_location("ditreeonlineplanner_b200.planners.RRT", os.environ["OLD_RRT"])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ditreeonlineplanner_b200.planners.RRT"] = mod
+    spec.loader.exec_module(mod)
 ctx = get_context(0)
 sd = random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=UNET_DIMS["large"])
 sampler = DiffusionSampler(sd, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2, obs_history=1,
@@ -22,4 +29,4 @@ table, secs = sc.run_suite(sampler, total_runs=2, time_budget=1e9, planner_kwarg
 pr.disable()
 torch.cuda.synchronize()
 print(f"{len(table)} units in {time.time()-t0:.2f} s -> {len(table)/(time.time()-t0):.2f} units/s")
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+pstats.Stats(pr).sort_stats("tottime").print_stats(12)

@@ -954,6 +954,38 @@ static int unet_body(dt_ctx* ctx, dt_denoiser* d, int64_t B, const float* film_t
 static int enc_conv(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bfloat16* in, int64_t B, int H, int W,
                     int Cin, int k, int stride, int pad, int OH, int OW, __nv_bfloat16* out, cudaStream_t st) {
   const int64_t rows = B * OH * OW;
+  if (OH == 1 && OW == 1 && H * W <= GEMM_MAX_SEG && Cin % 64 == 0 && w.Ktot == k * k * Cin) {
+    // One output pixel per sample (the last ResNet stage on small local maps): the taps that land on the
+    // zero padding contribute nothing, and the ones that land on the map meet its pixels in row-major order,
+    // so the input itself is the GEMM's A operand -- (B, H W, Cin) read as H W "time steps" -- and each valid
+    // tap is one K segment over its own slice of the packed weights.  No im2col, K = (valid taps) x Cin
+    // instead of k k Cin (512 instead of 4608 on a 1 x 1 map); the dropped products were exact zeros.
+    ConvGemm g;
+    g.a[0] = ActSrc{in, Cin, H * W, 1};
+    g.n_src = 1;
+    g.w = w.w;
+    g.w_ktot = w.Ktot;
+    g.N = w.N;
+    g.nseg = 0;
+    int next_tap = 0;  // first weight tap not yet consumed or skipped
+    for (int ky = 0; ky < k; ++ky) {
+      for (int kx = 0; kx < k; ++kx) {
+        const int iy = ky - pad, ix = kx - pad;  // output pixel (0, 0): input pixel (iy, ix), any stride
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const int tap = ky * k + kx;
+        g.seg[g.nseg++] = GemmSeg{0, 0, iy * W + ix, Cin / 64, (tap - next_tap) * (Cin / 64)};
+        next_tap = tap + 1;
+      }
+    }
+    g.B = B;
+    g.T = 1;
+    g.epi = EPI_PLAIN;
+    g.bias = w.bias;
+    g.out_bf16 = out;
+    g.ldc = w.N;
+    g.out_b_stride = 1;
+    return dt_conv_gemm(ctx, g, st);
+  }
   if (Cin % 8 == 0 && w.Ktot == k * k * Cin) {
     k_im2col_v8<<<ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
     DT_LAUNCH_CHECK("k_im2col_v8");

@@ -333,10 +333,11 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         b_base = m_tile * g.nb;
         t_base = 0;
       }
-      int kw = 0;
+      int kw = 0, wofs = 0;
       for (int s = 0; s < g.nseg; ++s) {
         const GemmSeg sg = g.seg[s];
         const CUtensorMap* mA = sg.src ? &mapA1 : &mapA0;
+        wofs += sg.w_gap;  // weight blocks this launch leaves out
         for (int blk = 0; blk < sg.nblk; ++blk, ++kw) {
           if (kw < kb0 || kw >= kb1) continue;  // another K slice's block
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -346,11 +347,11 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
               // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
               if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * P::kStage);
               tma2_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
-              tma2_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN + (int)rank * (BN / 2));
+              tma2_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, (kw + wofs) * BK, n_tile * BN + (int)rank * (BN / 2));
             } else {
               mbar_expect_tx(bar_full + 8 * stage, P::kStage);
               tma_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
-              tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, kw * BK, n_tile * BN);
+              tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, (kw + wofs) * BK, n_tile * BN);
             }
           }
           __syncwarp();
@@ -1105,7 +1106,7 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   const int rows = (int)(g.B * g.T);
   const int bn = (g.N % 256 == 0) ? 256 : ((g.N % 128 == 0) ? 128 : 64);
   const int n_tiles = (g.N / bn) * (flat ? (rows + BM - 1) / BM : 1);
-  if (nkb < (flat ? 64 : 8) || n_tiles * 4 > ctx->sm_count) return 0;  // flat: measured win only from K = 4096 up (35 -> 27 us)
+  if (nkb < (flat ? 64 : 12) || n_tiles * 4 > ctx->sm_count) return 0;  // flat: measured win only from K = 4096 up (35 -> 27 us)
   int ksplit = ctx->sm_count / n_tiles;              // one work item per SM
   if (flat) {                                        // several tiles: the reduction reads ksplit x the output,
     if (ksplit > nkb / 4) ksplit = (int)(nkb / 4);   // keep the slices long and few
@@ -1249,7 +1250,7 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   }
   // CTA pairs need at least two 128-row tiles; tiny problems stay on one CTA
   const int cg = (d.num_m_tiles >= 2) ? gemm_cta_group() : 1;
-  rc = make_w_map(ctx, &mW, g.w, g.N, ktot, bn / cg);
+  rc = make_w_map(ctx, &mW, g.w, g.N, g.w_ktot > 0 ? g.w_ktot : ktot, bn / cg);
   if (rc) return rc;
 
   if (g.epi == EPI_PLAIN) {

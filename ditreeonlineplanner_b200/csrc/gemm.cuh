@@ -10,6 +10,9 @@ struct GemmSeg {
   int phase;  // time phase inside the (T/P, P) view
   int t_off;  // time offset in units of the P-strided axis
   int nblk;   // number of 64-channel K blocks
+  int w_gap;  // weight K blocks skipped before this segment (0 = the weights follow the previous segment's);
+              // lets a launch use a subset of a packed conv's taps (2-D convs on 1 x 1 / 2 x 2 maps: the taps that
+              // only ever see zero padding are left out)
 };
 
 #define GEMM_MAX_SEG 8
@@ -29,6 +32,7 @@ struct ConvGemm {
   int n_src = 1;
   const __nv_bfloat16* w = nullptr;  // packed weights [N][Ktot] bf16, K-major; Ktot = 64 * sum(nblk)
   int N = 0;                         // output channels (multiple of the N tile)
+  int64_t w_ktot = 0;                // row length of `w` in elements when segments skip blocks (0 = 64 * sum(nblk))
   int nseg = 0;
   GemmSeg seg[GEMM_MAX_SEG];
   // ---- row geometry -----------------------------------------------------------------------

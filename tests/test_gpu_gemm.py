@@ -25,3 +25,25 @@ def test_gemm_bf16(ctx, M, N, K):
     err = (got - want).abs().max().item()
     scale = want.abs().max().item()
     assert err <= 2e-3 * scale + 1e-3, f"max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 4608), (300, 512, 4608), (64, 512, 4608), (1000, 256, 4096), (8, 64, 8192)])
+def test_gemm_split_k_shapes(ctx, M, N, K):
+    """Few tiles and a long K: the split-K work items + the reduce kernel (one-tile and flat multi-tile
+    forms), against fp32 matmul and against the unsplit kernel (`splitk` option off)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    want = a.float() @ w.float().t()
+    scale = want.abs().max().item()
+    try:
+        ctx.set_option("splitk", 1)
+        split = ctx.gemm_bf16(a, w)
+        ctx.set_option("splitk", 0)
+        plain = ctx.gemm_bf16(a, w)
+    finally:
+        ctx.set_option("splitk", 1)
+    torch.cuda.synchronize()
+    assert (split - want).abs().max().item() <= 1e-4 * scale
+    assert (plain - want).abs().max().item() <= 1e-4 * scale
+    assert (split - plain).abs().max().item() <= 2e-5 * scale   # same products, another summation order

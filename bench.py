@@ -276,7 +276,9 @@ def main():
         suite_kw = {"batch_size": 256, "iteration_cap": 256 * 8 * 2}  # 8 passes per slot group = one full 64-step edge per slot
         # untimed warm-up unit: builds the planner's second device context, captures its graphs
         sc.run_car_unit(sc.load_scenarios("test_scenarios_car")[0], 0, 0, sampler, 1e9, suite_kw)
+        from ditreeonlineplanner_b200.planners import RRT as rrt_mod
         barrier()
+        rrt_mod.PASS_STATS.update(gpu_wait_s=0.0, passes=0)
         t0 = time.perf_counter()
         table, _ = sc.run_suite(sampler, total_runs=args.suite_runs, time_budget=1e9, rank=rank, world=world,
                                 device=ctx.device, planner_kwargs=suite_kw)
@@ -285,11 +287,21 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rows_t = np.array(list(table.values()))
+        mine = torch.tensor([rrt_mod.PASS_STATS["gpu_wait_s"], float(rrt_mod.PASS_STATS["passes"])], device="cuda",
+                            dtype=torch.float64)
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, mine)
+        else:
+            per_rank = [mine]
         suite = {"units": len(table), "scenarios_per_s": len(table) / float(t.item()), "seconds": float(t.item()),
                  "unit": "one (scenario, run) of test_scenarios_car: batched RRT with continuous slot refill, 2 x 256 slots on two streams, "
                          "4096 chunk expansions (the reference's iteration count) or goal, K=1 (the reference's "
                          "planning_diffusion_iters), large denoiser",
                  "unit_seconds_sum": float(rows_t[:, 2].sum()),
+                 "device_wait_seconds_per_rank": [round(float(p_[0]), 3) for p_ in per_rank],
+                 "passes_per_rank": [int(p_[1]) for p_ in per_rank],
+                 "host": {"cpus": os.cpu_count(), "loadavg": list(os.getloadavg())},
                  "mean_tree_nodes": float(np.mean(rows_t[:, 6][rows_t[:, 6] > 0])) if (rows_t[:, 6] > 0).any() else 0.0,
                  "schedule": "ranks pull units from one shared counter (process-group store), heaviest maps first",
                  "gather": "one all_gather of [units, 13] fp32 rows"}

@@ -24,6 +24,10 @@ from ..common.map_utils import _ctx_for
 from .base_planner import BasePlanner, Node
 
 
+# host seconds spent waiting for device passes / passes booked by the continuous planner in this process
+# (bench.py reports them per rank next to the suite throughput: device-bound vs host-bound at a glance)
+PASS_STATS = {"gpu_wait_s": 0.0, "passes": 0}
+
 class _DeviceTree:
     """SoA mirror of the node positions in HBM (x[], y[]) for the nearest-neighbour kernel; replaces
     the KD-tree the reference rebuilds from scratch after every insertion (RRT.py:207)."""
@@ -369,7 +373,10 @@ class RRT_Planner(BasePlanner):
 
         def harvest(g):
             """Book one finished pass of group g; returns the goal node if some slot reached the goal."""
+            t_wait = time.perf_counter()
             g.event.synchronize()
+            PASS_STATS["gpu_wait_s"] += time.perf_counter() - t_wait
+            PASS_STATS["passes"] += 1
             g.in_flight = False
             out = g.h_out.numpy().astype(np.float64)
             traj = out[:, :h * 6].reshape(B, h, 6)

@@ -54,6 +54,15 @@ def test_partition_is_exact_cover():
         assert max(sizes) - min(sizes) <= 1  # unit-level sharding balances 150 units over 8 ranks
 
 
+def test_queue_order_is_heaviest_first_and_complete():
+    w = [9, 400, 25, 400, 961]
+    order = sc.all_units(5, 3, w, by_weight=True)
+    assert sorted(order) == sorted(sc.all_units(5, 3)) and len(set(order)) == 15
+    assert [s for s, _ in order[:3]] == [4, 4, 4] and [r for _, r in order[:3]] == [0, 1, 2]  # all runs of the largest map first
+    weights_seen = [w[s] for s, _ in order]
+    assert weights_seen == sorted(weights_seen, reverse=True)
+
+
 def test_unit_seeds_are_world_size_invariant():
     seeds = {(s, r): sc.unit_seed(s, r) for s in range(15) for r in range(10)}
     assert len(set(seeds.values())) == 150

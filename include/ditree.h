@@ -47,9 +47,11 @@ const char* dt_last_error(dt_ctx* ctx);
 const char* dt_version(void);
 
 /* Tuning switches.  "splitk" (default 1): conv GEMMs with at most 128 rows (sampler batches of 1-2 candidates,
- * the reference's own B = 1 loop) split K over all SMs and reduce in a second kernel -- ~2x less latency, but a
+ * the reference's own B = 1 loop) and flat few-tile GEMMs with K >= 4096 (the map encoder's last stage at a few
+ * hundred candidates) split K over all SMs and reduce in a second kernel -- ~2x less latency, but a
  * candidate's bits then depend on whether it was sampled alone or in a batch (different fp32 summation order,
- * same 2e-2 tolerance).  0 restores batch-size independent results. */
+ * same 2e-2 tolerance).  0 restores batch-size independent results.  Changing the value synchronises the
+ * device and drops the captured sampler graphs (they bake in the kernel selection). */
 int dt_set_option(dt_ctx* ctx, const char* name, int value);
 
 /* Occupancy grid upload.  Replaces RRT_Planner.update_maze / BasePlanner.maze

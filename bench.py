@@ -106,48 +106,103 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle port): same pipeline, bounded sample
 # ---------------------------------------------------------------------------------------------
+CPU_SAMPLE = 64  # candidates per CPU step: fixed, independent of --steps (a 9-candidate step ran torch-CPU convs at 40 %
+                 # of the throughput of a 64-candidate one and inflated the GPU / CPU ratio)
+
+
+def bench_config(args, workload):
+    """The `config` object BOTH arms print (the driver checks that they are the same)."""
+    return {"workload": workload, "candidates_per_gpu": args.batch, "ode_steps": args.ode_steps,
+            "rollout_steps": args.rollout,
+            "l2_policy": "working set per step (activations ~7 GB, weights 0.37 GB) exceeds the 126 MB L2; no flush needed",
+            "weights": "random-init, reference architecture (184 M parameters)",
+            "reference_arm_sample": f"{CPU_SAMPLE} candidates of the same workload per CPU step (the full 4096 would take "
+                                    "minutes per step on the host); edges/s = candidates / time"}
+
+
 def cpu_expansion_factory(args, grid, meta):
+    """-> (run(st, prev, seed), kind).  kind "reference": the UNMODIFIED reference staged in oracle/_ref (see
+    oracle/build_ref.py) through its own API -- create_local_map, DiffusionSampler.forward (one batched call, torch CPU
+    on all host threads), then its per-candidate propagate_action_sequence_env loop; kind "port": the oracle's
+    restatement of the same functions, when oracle/_ref is not staged."""
     from oracle import denoiser_ref as dref
     from oracle import ditree_oracle as orc
+    from oracle import ref_arm
     from ditreeonlineplanner_b200.weights import UNET_DIMS
     dims = UNET_DIMS[args.denoiser]
     sd = dref.init_params(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims)
     R, C = grid.shape
     goal = goal_of(grid)
+    if ref_arm.available() and os.environ.get("DITREE_CPU_ARM", "reference") == "reference":
+        run_ref = ref_arm.Reference().expansion(grid, sd, dims, args.ode_steps, args.rollout, goal)
+        return (lambda st, prev, seed: run_ref(st, prev, seed=seed)), "reference"
 
-    def run(st, prev, noise):
+    def run(st, prev, seed):
         s64 = st.astype(np.float64)
+        noise = torch.randn((len(st), 64, 2), generator=torch.Generator().manual_seed(seed))
         lm = orc.local_map(grid, s64[:, 0], s64[:, 1], s64[:, 2], 20, 0.2, 1.0, (C / 2, R / 2))
         cond = orc.build_cond_car(s64, prev.astype(np.float64), goal, meta, 20.0)
-        act = dref.fm_sample(sd, torch.from_numpy(noise), torch.from_numpy(cond), torch.from_numpy(lm), args.ode_steps,
+        act = dref.fm_sample(sd, noise, torch.from_numpy(cond), torch.from_numpy(lm), args.ode_steps,
                              meta["Actions_mean"], meta["Actions_std"])
         return orc.rollout_car(s64, act[:, :args.rollout], goal, grid)
-    return run
+    return run, "port"
 
 
-def time_cpu(args, grid, meta, budget_s=15.0, steps=1, warmup=0):
-    run = cpu_expansion_factory(args, grid, meta)
+def time_cpu(args, grid, meta, steps=1, warmup=1):
+    run, kind = cpu_expansion_factory(args, grid, meta)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    rng = np.random.default_rng(1)
-    n = 2
-    st, prev = synth_candidates(grid, n, 7)
-    t0 = time.perf_counter()
-    run(st, prev, rng.standard_normal((n, 64, 2)).astype(np.float32))
-    per = (time.perf_counter() - t0) / n
-    n = int(max(2, min(64, budget_s / max(per, 1e-3) / max(1, steps + warmup))))
+    n = CPU_SAMPLE
     st, prev = synth_candidates(grid, n, 8)
-    noise = rng.standard_normal((n, 64, 2)).astype(np.float32)
-    for _ in range(warmup):
-        run(st, prev, noise)
+    for w in range(warmup):
+        run(st, prev, 100 + w)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        run(st, prev, noise)
+    for i in range(steps):
+        run(st, prev, 200 + i)
     el = time.perf_counter() - t0
-    return dict(value=n * steps / el, unit=UNIT, cores=cores, kind="port",
-                sample=f"{n} candidates x {steps} step(s) of the same workload (K={args.ode_steps} ODE steps, "
-                       f"{args.denoiser} denoiser in torch-CPU fp32 on {torch.get_num_threads()} threads, "
-                       f"{args.rollout}-step NumPy rollout + collision)"), el / steps * 1e3
+    what = ("the unmodified reference (oracle/_ref: create_local_map, DiffusionSampler.forward batched over the sample, "
+            "then its per-candidate propagate_action_sequence_env loop)") if kind == "reference" else \
+        "the oracle port (NumPy / torch-CPU restatement; oracle/_ref not staged)"
+    return dict(value=n * steps / el, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{n} candidates x {steps} timed step(s) after {warmup} warm-up of the same workload (K={args.ode_steps} ODE "
+                       f"steps, {args.denoiser} denoiser in torch-CPU fp32 on {torch.get_num_threads()} threads, "
+                       f"{args.rollout}-step rollout + collision per candidate) by {what}"), el / steps * 1e3
+
+
+def parity_check(args, grid, meta, sd, st_np, prev_np, noise, res, n_check=32):
+    """Untimed: n_check of the step's candidates (spread over the batch, so over different tiles and CTA pairs)
+    recomputed by the fp32 oracle from the same states / noise; denoiser output compared on the NORMALISED sample
+    (tolerance 2e-2, north star), flags bit-exact given the device's own trajectory."""
+    from oracle import denoiser_ref as dref
+    from oracle import ditree_oracle as orc
+    B = st_np.shape[0]
+    idx = np.unique(np.linspace(0, B - 1, n_check).astype(np.int64))
+    R, C = grid.shape
+    goal = goal_of(grid)
+    s64 = st_np[idx].astype(np.float64)
+    lm = orc.local_map(grid, s64[:, 0], s64[:, 1], s64[:, 2], 20, 0.2, 1.0, (C / 2, R / 2))
+    cond = orc.build_cond_car(s64, prev_np[idx].astype(np.float64), goal, meta, 20.0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    want = dref.fm_sample(sd, noise[idx].cpu(), torch.from_numpy(cond), torch.from_numpy(lm), args.ode_steps)
+    didx = torch.as_tensor(idx, device=res["actions"].device)
+    got_act = res["actions"][didx].cpu().numpy().astype(np.float64)
+    got = (got_act - meta["Actions_mean"]) / meta["Actions_std"]
+    rel = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    worst = float(max(np.linalg.norm(got[i] - want[i]) / np.linalg.norm(want[i]) for i in range(len(idx))))
+    S = args.rollout
+    traj = res["traj"][didx].cpu().numpy()
+    forced = orc.rollout_car(s64, got_act[:, :S], goal, grid, states_for_flags=traj)
+    flags_ok = bool(np.array_equal(forced["first_coll"], res["first_coll"][didx].cpu().numpy()) and
+                    np.array_equal(forced["done_step"], res["done_step"][didx].cpu().numpy()))
+    free = orc.rollout_car(s64, got_act[:, :S], goal, grid)
+    keep = forced["first_coll"] < 0
+    st_rel = float(np.linalg.norm(res["final"][didx].cpu().numpy()[keep] - free["final"][keep]) /
+                   max(np.linalg.norm(free["final"][keep]), 1e-30)) if keep.any() else 0.0
+    return {"candidates_checked": int(len(idx)), "rel_err": rel, "worst_candidate_rel_err": worst, "tolerance": 2e-2,
+            "flags_bit_exact": flags_ok, "final_state_rel_err": st_rel, "state_tolerance": 1e-4,
+            "what": "normalised K-step denoiser sample vs the fp32 oracle on the same states / noise (norm-relative); "
+                    "collision / goal flags vs the float64 oracle given the device trajectory; final states of the "
+                    "collision-free edges vs the float64 oracle rollout of the device's actions"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,15 +232,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb, ms = time_cpu(args, grid, meta, budget_s=60.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+        cb, ms = time_cpu(args, grid, meta, steps=max(1, args.steps), warmup=max(0, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "candidates_per_gpu": args.batch, "ode_steps": args.ode_steps,
-                           "rollout_steps": args.rollout,
-                           "weights": "random-init, reference architecture (184 M parameters)",
-                           "note": "reference CPU path = NumPy/torch-CPU oracle port; the Python reference itself "
-                                   "cannot travel to the GPU box; each step is the bounded sample named in cpu_baseline"},
+                "config": bench_config(args, workload),
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -252,14 +303,15 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = world * B / (ms_step * 1e-3)
     ok_edges = int((res["first_coll"] < 0).sum().item())
+    parity = parity_check(args, grid, meta, sd, st_np, prev_np, noise, res) if rank == 0 else None
 
     # ---------------- e2e through the host-facing API ----------------
     for _ in range(2):
-        exp.expand(st_np, prev_np, goal)
+        exp.expand(st_np, prev_np, goal, want_traj=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, h2d, d2h = exp.expand(st_np, prev_np, goal)
+        out, h2d, d2h = exp.expand(st_np, prev_np, goal, want_traj=True)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -396,17 +448,17 @@ def main():
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:
-        cb, _ = time_cpu(args, grid, meta, budget_s=15.0)
+        cb, _ = time_cpu(args, grid, meta, steps=3, warmup=1)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload, "candidates_per_gpu": B, "ode_steps": args.ode_steps, "rollout_steps": S,
-                       "l2_policy": "working set per step (activations ~7 GB, weights 0.37 GB) exceeds the 126 MB L2; no flush needed",
-                       "weights": "random-init, reference architecture (184 M parameters)"},
+            "config": bench_config(args, workload),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "TreeExpander.expand(states, prev_actions, goal) with NumPy host arrays"},
-            "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges,
+                    "ms_per_step": e2e_ms, "api": "TreeExpander.expand(states, prev_actions, goal, want_traj=True) with NumPy host arrays; the "
+                           "D2H side returns what propagate_action_sequence_env returns: final states, flags, the "
+                           "executed actions and the (B, S, 6) state sequences"},
+            "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges, "parity_check": parity,
             "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "suite": suite,
             "clocks": clocks.summary()}
     emit(line)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "dt_sample_cells": (C.c_int, [c_p, c_p, C.c_int, c_p, c_i64, c_p, c_p]),
     "dt_ray_probe": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dt_path_first_obstacle": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "dt_path_first_obstacle_grid": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dt_lidar_scan": (C.c_int, [c_p, c_p, c_i64, c_p, c_p, c_p, c_p]),
     "dt_propagate_collide": (C.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, C.c_int, C.c_float,
                                        C.c_float, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, C.c_int, c_p]),

@@ -48,7 +48,7 @@ struct dt_ctx {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
   size_t prof_used = 0;
-  struct ProfRec { int bn, epi, gw; long long M; int N; long long K; float ms; };
+  struct ProfRec { int bn, epi, gw; long long M; int N; long long K; float ms; int ksplit; };  // epi 2 = k_splitk_epi
   std::vector<ProfRec> prof_recs;
 };
 

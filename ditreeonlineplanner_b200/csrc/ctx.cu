@@ -94,12 +94,12 @@ extern "C" int dt_profile_csv(dt_ctx* ctx, const char* path) {
   if (!ctx || !path) return DT_E_ARG;
   FILE* f = fopen(path, "w");
   if (!f) return dt_fail(ctx, DT_E_ARG, "dt_profile_csv: cannot open file");
-  fprintf(f, "idx,BN,epi,gw,M,N,K,ms,tflops\n");
+  fprintf(f, "idx,BN,epi,gw,M,N,K,ms,tflops,ksplit\n");
   for (size_t i = 0; i < ctx->prof_recs.size(); ++i) {
     const dt_ctx::ProfRec& r = ctx->prof_recs[i];
     const double fl = 2.0 * (double)r.M * r.N * (double)r.K;
-    fprintf(f, "%zu,%d,%d,%d,%lld,%d,%lld,%.5f,%.1f\n", i, r.bn, r.epi, r.gw, r.M, r.N, r.K, r.ms,
-            r.ms > 0 ? fl / (r.ms * 1e-3) / 1e12 : 0.0);
+    fprintf(f, "%zu,%d,%d,%d,%lld,%d,%lld,%.5f,%.1f,%d\n", i, r.bn, r.epi, r.gw, r.M, r.N, r.K, r.ms,
+            (r.ms > 0 && r.epi != 2) ? fl / (r.ms * 1e-3) / 1e12 : 0.0, r.ksplit);
   }
   fclose(f);
   return DT_OK;

@@ -834,7 +834,7 @@ static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap&
     e0 = dt_prof_event(ctx);
     e1 = dt_prof_event(ctx);
     if (e0 && e1) {
-      dt_ctx::ProfRec rec{BN, EPI, GW * 10 + CG, (long long)d.B * d.T, d.N, (long long)d.nkb_total * BK, 0.f};
+      dt_ctx::ProfRec rec{BN, EPI, GW * 10 + CG, (long long)d.B * d.T, d.N, (long long)d.nkb_total * BK, 0.f, d.ksplit};
       ctx->prof_recs.push_back(rec);
       cudaEventRecord(e0, st);
     }
@@ -1094,7 +1094,7 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);
 
 // -> 0 = not applicable (caller continues with the fused path), 1 = done, negative = error
 static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
-  if (!ctx->splitk_on || ctx->prof_on || g.ksplit > 1) return 0;
+  if (!ctx->splitk_on || g.ksplit > 1) return 0;
   // two shapes qualify: (a) whole samples inside ONE 128-row tile (the U-Net at a few candidates), and
   // (b) a flat [rows, N] problem -- one "sample", plain epilogue -- with a handful of 128-row tiles and a
   // long K (the encoder's last stages at planner batch sizes: 256 x 512 x 4608 is four tiles on 148 SMs)
@@ -1165,7 +1165,18 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->prof_on) {  // the reduction is part of the layer's cost: recorded as epi = 2 (no flops of its own)
+    e0 = dt_prof_event(ctx);
+    e1 = dt_prof_event(ctx);
+    if (e0 && e1) {
+      dt_ctx::ProfRec rec{0, 2, e.gw * 10 + cs, (long long)rows, g.N, nkb * BK, 0.f, ksplit};
+      ctx->prof_recs.push_back(rec);
+      cudaEventRecord(e0, st);
+    }
+  }
   DT_CUDA(cudaLaunchKernelEx(&cfg, k_splitk_epi, e));
+  if (e0 && e1) cudaEventRecord(e1, st);
   DT_LAUNCH_CHECK("k_splitk_epi");
   return 1;
 }

@@ -358,6 +358,32 @@ k_path_first_obstacle(MapView m, const float* __restrict__ x, const float* __res
   if (threadIdx.x == 0) idx_out[0] = (best == 0x7fffffff) ? -1 : best;
 }
 
+// the same against a caller-supplied grid in global memory (a few hundred bytes, read through L1 / L2)
+__global__ void __launch_bounds__(GEOM_THREADS)
+k_path_first_obstacle_grid(const uint8_t* __restrict__ grid, int rows, int cols, const float* __restrict__ x,
+                           const float* __restrict__ y, int64_t stride, int64_t n, int32_t* __restrict__ idx_out,
+                           int* __restrict__ status) {
+  __shared__ int best;
+  if (threadIdx.x == 0) best = 0x7fffffff;
+  __syncthreads();
+  const double cx = xdiv((double)cols, 2.0), cy = xdiv((double)rows, 2.0);
+  int mine = 0x7fffffff;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    int r = dt_floor_i(xsub(cy, (double)y[i * stride]));
+    int c = dt_floor_i(xadd((double)x[i * stride], cx));
+    if (r < 0) r += rows;  // NumPy negative indices wrap
+    if (c < 0) c += cols;
+    if (r < 0 || r >= rows || c < 0 || c >= cols) {
+      atomicMin(status, DT_E_INDEX);
+      continue;
+    }
+    if (grid[r * cols + c] == 1 && (int)i < mine) mine = (int)i;
+  }
+  atomicMin(&best, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) idx_out[0] = (best == 0x7fffffff) ? -1 : best;
+}
+
 // -------------------------------------------------------------------------------------------
 // Lidar2DSim.scan  (lidar_sim/lidar_2d_sim.py:18-98): one warp per bundle of 32 rays
 // -------------------------------------------------------------------------------------------
@@ -593,6 +619,17 @@ extern "C" int dt_path_first_obstacle(dt_ctx* ctx, const float* x, const float* 
   k_path_first_obstacle<<<1, GEOM_THREADS, m.bytes, (cudaStream_t)stream>>>(m, x, y, stride, n, idx_out,
                                                                            ctx->d_status);
   DT_LAUNCH_CHECK("k_path_first_obstacle");
+  return DT_OK;
+}
+
+extern "C" int dt_path_first_obstacle_grid(dt_ctx* ctx, const uint8_t* grid_u8, int rows, int cols, const float* x,
+                                           const float* y, int64_t stride, int64_t n, int32_t* idx_out, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!idx_out || !grid_u8 || rows <= 0 || cols <= 0) return dt_fail(ctx, DT_E_ARG, "dt_path_first_obstacle_grid: bad argument");
+  if (n > 0 && (!x || !y)) return dt_fail(ctx, DT_E_ARG, "dt_path_first_obstacle_grid: null pointer");
+  k_path_first_obstacle_grid<<<1, GEOM_THREADS, 0, (cudaStream_t)stream>>>(grid_u8, rows, cols, x, y, stride, n, idx_out,
+                                                                          ctx->d_status);
+  DT_LAUNCH_CHECK("k_path_first_obstacle_grid");
   return DT_OK;
 }
 

@@ -28,6 +28,9 @@ class Lidar2DSim:
         return d[0], e[0], np.stack([xs, ys], 1)
 
     def scan_batch(self, poses, maze_data):
+        """The kernel marches the rays in float64 from a float32 pose (the device state format; the reference keeps
+        the pose in float64): hit cells are exact and distances within 1e-5 for float32-representable poses, which
+        is what the planner's float32 states are."""
         ctx = _ctx_for(maze_data, 1.0)
         poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float32)[:, :3])
         dist, end, vis = ctx.lidar_scan(torch.as_tensor(poses))
@@ -41,7 +44,5 @@ class Lidar2DSim:
             end = np.stack([poses[:, 0:1] + nd * np.cos(ang), poses[:, 1:2] + nd * np.sin(ang)], -1)
             dist = nd
         else:
-            for _ in range(dist.size):  # keep NumPy's global RNG stream aligned with the reference
-                pass
-            np.random.normal(0, 1.0, dist.size)
+            np.random.normal(0, 1.0, dist.size)  # keeps NumPy's global RNG stream aligned with the reference (:31)
         return dist, end, vis

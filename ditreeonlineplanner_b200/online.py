@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .common.map_utils import _ctx_for
+from .runtime import get_context
 
 
 def scan_and_update_maze(planner, maze_data, maze_data_with_obstacle, scanned_maze, debug=False):
@@ -30,10 +30,12 @@ def scan_and_update_maze(planner, maze_data, maze_data_with_obstacle, scanned_ma
 
 
 def check_no_obstacles_in_path(planner, scanned_maze, main_path_array, debug=False):
-    """Index of the first path point lying in a scanned obstacle cell, -1 if the path is clear."""
-    ctx = _ctx_for(np.asarray(scanned_maze, dtype=np.float32), 1.0)
+    """Index of the first path point lying in a scanned obstacle cell, -1 if the path is clear.  The scanned map
+    (0 unknown / 1 obstacle / 2 seen) travels with the path as a kernel argument: the planner's staged map stays
+    resident (one upload of rows*cols bytes per scan instead of two map re-stagings)."""
+    ctx = get_context()
     path = np.ascontiguousarray(np.asarray(main_path_array, dtype=np.float32)[:, :2])
-    idx = int(ctx.path_first_obstacle(torch.as_tensor(path))[0])
+    idx = int(ctx.path_first_obstacle_grid(np.asarray(scanned_maze).astype(np.uint8), torch.as_tensor(path))[0])
     ctx.sync_status()
     return idx
 

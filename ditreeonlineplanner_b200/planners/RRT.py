@@ -295,7 +295,7 @@ class RRT_Planner(BasePlanner):
         self._ctx = _ctx_for(self.maze, self.s_global)
         dev = ctx.device
         group_ctx = [ctx, smp._twin_context(B)]
-        group_ctx[1].set_map(np.float32(self.maze), self.s_global)
+        group_ctx[1].set_map(np.float32(self.maze), self.s_global)   # synchronous; every earlier plan() drained its streams
         h = self.action_horizon
         A = smp.action_dim
         mean_np = smp.metadata["Actions_mean"].astype(np.float32)
@@ -415,31 +415,35 @@ class RRT_Planner(BasePlanner):
                 has_obstacle_ahead.extend(self.check_obstacle_ahead(nd.state) for nd in new_nodes)
             return goal_node, free
 
-        for g in groups:
-            refill(g, list(range(B)))
-        turn = 0
-        while (time.time() - start_time) < self.time_budget:
-            if self.iteration_cap is not None and iter_num >= self.iteration_cap:
-                break
-            g = groups[turn]
-            turn ^= 1
-            if g.in_flight:
-                goal_node, free = harvest(g)
-                if goal_node is not None:
-                    for gg in groups:
-                        gg.stream.synchronize()
-                    self.env.prob_map = orig_prob_map
-                    return self.handle_goal_reached(goal_node, iter_num, start_time)
-                refill(g, free)
-            launch(g)
-            iter_num += B
-        for g in groups:                          # book what is still in flight
-            if g.in_flight:
-                goal_node, _ = harvest(g)
-                if goal_node is not None:
-                    self.env.prob_map = orig_prob_map
-                    return self.handle_goal_reached(goal_node, iter_num, start_time)
-        return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)
+        try:
+            for g in groups:
+                refill(g, list(range(B)))
+            turn = 0
+            while (time.time() - start_time) < self.time_budget:
+                if self.iteration_cap is not None and iter_num >= self.iteration_cap:
+                    break
+                g = groups[turn]
+                turn ^= 1
+                if g.in_flight:
+                    goal_node, free = harvest(g)
+                    if goal_node is not None:
+                        self.env.prob_map = orig_prob_map
+                        return self.handle_goal_reached(goal_node, iter_num, start_time)
+                    refill(g, free)
+                launch(g)
+                iter_num += B
+            for g in groups:                          # book what is still in flight
+                if g.in_flight:
+                    goal_node, _ = harvest(g)
+                    if goal_node is not None:
+                        self.env.prob_map = orig_prob_map
+                        return self.handle_goal_reached(goal_node, iter_num, start_time)
+            return self._finish_without_goal(has_obstacle_ahead, iter_num, start_time, orig_prob_map)
+        finally:
+            # Whatever the exit (goal in either loop, budget, an exception), no pass may still be running on a
+            # group's arena, map or pinned buffers when the caller -- or the next plan() -- touches them again.
+            for g in groups:
+                g.stream.synchronize()
 
     # ---- batched expansion, one round of edges at a time ------------------------------------------
     def _plan_batched(self):

@@ -178,6 +178,13 @@ class BasePlanner(abc.ABC):
         self.env.current_step += (first + 1) if first >= 0 else ((done_step + 1) if done_step >= 0 else n)
         if first >= 0:
             states_sequence[1:first + 2] = traj[:first + 1]
+            # the reference's env.step ran its goal test (and, with collision_checking, its own collision test)
+            # on the colliding state BEFORE the planner saw the collision (car_env.py:264-272): both latches
+            # freeze every later propagation of this env
+            if self.env._goal_reached(obs[:2]):
+                self.env.done = True
+            if self.env.collision_checking:
+                self.env.terminated = True
             return obs, None, action_sequence[:first], states_sequence[:first][None, :]
         done = False
         if done_step >= 0:

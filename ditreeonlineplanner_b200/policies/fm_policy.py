@@ -28,6 +28,21 @@ def _infer_cfg(sd):
     return dims, emb, gdim - dsed - emb, A
 
 
+_tokens = []   # [(state_dict object, token)]: a monotonic token per distinct weights object, kept alive here so that
+_next_token = [0]  # an id() can never be recycled for another dict (what keying on id() alone would risk)
+
+
+def _weights_token(sd):
+    for obj, tok in _tokens:
+        if obj is sd:
+            return tok
+    _next_token[0] += 1
+    _tokens.append((sd, _next_token[0]))
+    if len(_tokens) > 8:      # bounded: old weights are released, their tokens never reused
+        _tokens.pop(0)
+    return _next_token[0]
+
+
 class DiffusionSampler(nn.Module):
     def __init__(self, noise_pred_net, noise_scheduler, env_id, policy, pred_horizon, action_dim,
                  prediction_type="actions", obs_history=1, action_history=1, num_diffusion_iters=100,
@@ -53,22 +68,27 @@ class DiffusionSampler(nn.Module):
         self._state_dict = noise_pred_net.state_dict() if hasattr(noise_pred_net, "state_dict") else dict(noise_pred_net)
         self._max_batch = max_batch
         self._ctx = None
+        self._key = None
 
     # nn.Module.to()/eval() keep working; the packed weights live in the device context
     def _context(self):
-        if self._ctx is None:
-            ctx = get_context()
+        """The process-wide device context with THIS sampler's weights packed in it.  Contexts are shared per
+        device, so another sampler (other weights, horizon or map size) may have re-packed it since the last call:
+        the key is compared on every call (one tuple comparison) and the weights are re-packed when it differs.
+        Samplers built from the same state_dict object share one key, hence one packing."""
+        ctx = get_context()
+        if self._key is None:
             dims, emb, cond_dim, A = _infer_cfg(self._state_dict)
             if A != self.action_dim:
                 raise ValueError(f"action_dim {self.action_dim} does not match the network ({A})")
-            key = (id(self._state_dict), self.pred_horizon, int(self.local_map_size), self._max_batch)
-            if getattr(ctx, "_loaded_key", None) != key:  # several samplers may share one set of weights
-                ctx.load_denoiser(self._state_dict, action_dim=A, horizon=self.pred_horizon, cond_dim=cond_dim,
-                                  emb_dim=emb, map_size=int(self.local_map_size), down_dims=dims,
-                                  max_batch=self._max_batch)
-                ctx._loaded_key = key
-            self._ctx = ctx
-        return self._ctx
+            self._cfg = dict(action_dim=A, horizon=self.pred_horizon, cond_dim=cond_dim, emb_dim=emb,
+                             map_size=int(self.local_map_size), down_dims=dims, max_batch=self._max_batch)
+            self._key = (_weights_token(self._state_dict), self.pred_horizon, int(self.local_map_size), self._max_batch)
+        if getattr(ctx, "_loaded_key", None) != self._key:
+            ctx.load_denoiser(self._state_dict, **self._cfg)
+            ctx._loaded_key = self._key
+        self._ctx = ctx
+        return ctx
 
     def _twin_context(self, max_batch):
         """A second device context holding the same packed weights (own activation arena), so two independent

@@ -91,6 +91,23 @@ class Context:
     def profile_csv(self, path):
         self._check(self.lib.dt_profile_csv(self.h, str(path).encode()))
 
+    def profile_records(self):
+        """Per-launch records of the last profile_begin/profile_end window: list of dicts with the CSV's columns
+        (BN, epi: 0 bias / 1 GroupNorm+Mish / 2 split-K reduction, gw = 10 * group width + CTAs per tile, M, N, K,
+        ms, tflops, ksplit)."""
+        import csv
+        import os
+        import tempfile
+        fd, path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        try:
+            self.profile_csv(path)
+            with open(path) as f:
+                return [{k: (float(v) if k in ("ms", "tflops") else int(v)) for k, v in row.items()}
+                        for row in csv.DictReader(f)]
+        finally:
+            os.unlink(path)
+
     @property
     def launches(self):
         return int(self.lib.dt_launch_count(self.h))
@@ -162,6 +179,17 @@ class Context:
         out = torch.empty(1, dtype=torch.int32, device=self.device)
         self._check(self.lib.dt_path_first_obstacle(self.h, _ptr(p[:, 0]), _ptr(p[:, 1]), p.stride(0), p.shape[0],
                                                     _ptr(out), self._stream()))
+        return out
+
+    def path_first_obstacle_grid(self, grid_u8, path_xy):
+        """Same test against a caller-supplied (rows, cols) uint8 grid (the online driver's scanned map, values
+        0 / 1 / 2) instead of the staged planner map, which stays resident."""
+        g = grid_u8 if isinstance(grid_u8, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(grid_u8, dtype=np.uint8))
+        g = g.to(self.device, torch.uint8).contiguous()
+        p = self._f32(path_xy)
+        out = torch.empty(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.dt_path_first_obstacle_grid(self.h, _ptr(g), g.shape[0], g.shape[1], _ptr(p[:, 0]),
+                                                         _ptr(p[:, 1]), p.stride(0), p.shape[0], _ptr(out), self._stream()))
         return out
 
     def lidar_scan(self, poses, want_visited=True):
@@ -335,6 +363,7 @@ class Context:
 
     # -- denoiser ---------------------------------------------------------------------------
     def load_denoiser(self, state_dict, action_dim, horizon, cond_dim, emb_dim, map_size, down_dims, max_batch):
+        self._loaded_key = None   # DiffusionSampler._context's cache key: whoever packs weights directly invalidates it
         keep = []
         descs = (L.TensorDesc * len(state_dict))()
         for i, (k, v) in enumerate(state_dict.items()):

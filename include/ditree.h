@@ -93,6 +93,13 @@ int dt_ray_probe(dt_ctx* ctx, const float* x, const float* y, const float* theta
 int dt_path_first_obstacle(dt_ctx* ctx, const float* x, const float* y, int64_t stride, int64_t n, int32_t* idx_out,
                            void* stream);
 
+/* The same test against a caller-supplied grid: grid_u8 is a DEVICE array of rows*cols bytes, row-major, compared
+ * with == 1 (the online driver's scanned map holds 0 = unknown, 1 = obstacle, 2 = seen free,
+ * run_scenarios_with_lidar_DiTree.py:120-122).  The ctx map is neither needed nor touched.  Map centre and cell
+ * size are the car's (cols/2, rows/2, 1 m). */
+int dt_path_first_obstacle_grid(dt_ctx* ctx, const uint8_t* grid_u8, int rows, int cols, const float* x, const float* y,
+                                int64_t stride, int64_t n, int32_t* idx_out, void* stream);
+
 /* Lidar2DSim.scan (lidar_sim/lidar_2d_sim.py:18-98, noise_std = 0) for B poses in GRID coordinates
  * (x = col, y = row, yaw): 181 rays each.  dist_out (B,181) f64, end_out (B,181,2) f64,
  * visited_out nullable (B, rows*cols) u8 mask of cells the rays crossed before their hit. */
@@ -222,7 +229,8 @@ int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, in
 int dt_profile_begin(dt_ctx* ctx);
 int dt_profile_end(dt_ctx* ctx, double* gemm_ms_out, int64_t* gemm_launches_out);
 /* Write the per-launch records of the last dt_profile_begin/end window as CSV
- * (index, BN, epilogue, group width, M rows, N, K, milliseconds, TFLOP/s). */
+ * (index, BN, epilogue: 0 bias / 1 GroupNorm+Mish / 2 the split-K reduction kernel, 10 * group width + CTAs per
+ * tile, M rows, N, K, milliseconds, TFLOP/s, K slices).  Split-K launches are recorded like any other. */
 int dt_profile_csv(dt_ctx* ctx, const char* path);
 
 /* Number of kernels this library launched since the ctx was created (bench.py's gpu_launches). */

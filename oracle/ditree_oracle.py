@@ -498,12 +498,27 @@ def ray_probe(state, maze):
 
 def path_first_obstacle(path_xy, scanned_maze):
     """run_scenarios_with_lidar_DiTree.py:158-181: index of the first path point whose floored
-    (col,row) cell equals 1 in the scanned map, else -1."""
+    (col,row) cell equals 1 in the scanned map, else -1.  Pinned by tests/golden/online.npz (the reference
+    function's own source, exec'ed by tools/gen_golden.py::gen_online, on 48 seeded paths)."""
     for idx, (x, y) in enumerate(np.asarray(path_xy, dtype=np.float64)[:, :2]):
         r, c = xy_to_rowcol(x, y, scanned_maze.shape, 1.0, floor=False)
         if scanned_maze[int(np.floor(r)), int(np.floor(c))] == 1:
             return idx
     return -1
+
+
+def scan_and_update_maze(state, known_maze, maze_with_obstacle, scanned_maze):
+    """run_scenarios_with_lidar_DiTree.py:112-127: lidar scan from the car's state (grid coordinates (col, row),
+    un-floored), hit cells -> 1 in the known and the scanned map, crossed cells -> 2 in the scanned map (hits win).
+    Updates the two maps in place; pinned by tests/golden/online.npz."""
+    r, c = xy_to_rowcol(state[0], state[1], known_maze.shape, 1.0, floor=False)
+    pose = np.array([c, r, state[2]], dtype=np.float64)
+    _, ends, visited = lidar_scan(pose, maze_with_obstacle)
+    ee = np.floor(ends).astype(int)
+    known_maze[ee[:, 1], ee[:, 0]] = 1
+    if len(visited):
+        scanned_maze[visited[:, 1], visited[:, 0]] = 2
+    scanned_maze[ee[:, 1], ee[:, 0]] = 1
 
 
 # --------------------------------------------------------------------------------------------

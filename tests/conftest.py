@@ -14,6 +14,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _have_b200():
+    try:
+        import torch
+        return torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need an sm_100 device: on any other box they are skipped (not failed), so a plain `pytest`
+    shows the CPU-runnable oracle / golden / host-logic tests green."""
+    if _have_b200():
+        return
+    skip = pytest.mark.skip(reason="needs a B200 (sm_100) CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 

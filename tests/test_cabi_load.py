@@ -52,3 +52,24 @@ def test_sass_is_sm100a():
     from ditreeonlineplanner_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_sass_opcodes_are_blackwell_native():
+    """The SASS of the built library, not the PTX source: every k_conv_gemm instantiation issues tcgen05.mma
+    (UTCHMMA; .2CTA in the CTA-pair ones), reads its accumulator with tcgen05.ld (LDTM) and loads tiles with TMA
+    (UTMALDG); the geometry kernels stage the occupancy grid with a bulk TMA copy (UBLKCP); nothing uses the
+    legacy mma.sync path (HMMA).  profiles/r02_sass_opcodes.md is this histogram, committed."""
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import sass_histogram as sh
+    per = sh.histogram()
+    gemm = {k: c for k, c in per.items() if "k_conv_gemm" in k}
+    assert len(gemm) >= 12, len(gemm)
+    for k, c in gemm.items():
+        assert c["UTCHMMA"] >= 4 and c["LDTM"] >= 2 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 2, (k, dict(c))
+        assert c["STL"] == 0 and c["LDL"] == 0, (k, "register spills in the GEMM kernel")
+    assert sum(1 for c in gemm.values() if c["UTCHMMA.2CTA"] >= 4) >= len(gemm) // 2
+    assert all(c["HMMA"] == 0 for c in per.values())
+    for name in ("k_propagate_rows", "k_collide_car4", "k_local_map", "k_lidar_scan"):
+        hit = [c for k, c in per.items() if name in k]
+        assert hit and all(c["UBLKCP"] >= 1 for c in hit), name

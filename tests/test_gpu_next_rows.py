@@ -79,6 +79,40 @@ def test_online_scan_and_path_check(mazes):
     assert check_no_obstacles_in_path(pl, scanned, clear) == -1
 
 
+def test_online_helpers_vs_reference_golden(mazes):
+    """The device path of check_no_obstacles_in_path / scan_and_update_maze against the reference's own functions
+    (golden online.npz).  The planner's staged map must survive the path check (it is not re-staged)."""
+    from conftest import golden
+    from ditreeonlineplanner_b200 import get_context
+    from ditreeonlineplanner_b200.car_env import CarEnv
+    from ditreeonlineplanner_b200.common.map_utils import _ctx_for
+    from ditreeonlineplanner_b200.lidar_sim.lidar_2d_sim import Lidar2DSim
+    from ditreeonlineplanner_b200.online import check_no_obstacles_in_path, scan_and_update_maze
+    import types
+    g = golden("online.npz")
+    base = mazes["boxes"].astype(np.float64)
+    ctx = _ctx_for(base, 1.0)
+    staged_before = ctx.map_shape
+    probe = torch.tensor([[0.5, 0.5, 0.0], [-9.5, -9.5, 0.0]])
+    flags_before = ctx.collide_car(probe).cpu().numpy()
+    for i in range(int(g["n_path"])):
+        got = check_no_obstacles_in_path(None, g[f"path{i}.scanned"].astype(np.float64), g[f"path{i}.path"])
+        assert got == int(g[f"path{i}.idx"]), i
+    assert get_context() is ctx and ctx.map_shape == staged_before
+    assert np.array_equal(ctx.collide_car(probe).cpu().numpy(), flags_before)
+    for i in range(int(g["n_scan"])):
+        env = CarEnv(maze_map=base.copy(), collision_checking=False)
+        env.lidar2dsim = Lidar2DSim(noise_std=0.0)
+        env.set_state(g[f"scan{i}.state"].copy())
+        seen = []
+        pl = types.SimpleNamespace(env=env, update_maze=lambda m: seen.append(m.copy()))
+        known, scanned = base.copy(), np.zeros_like(base)
+        scan_and_update_maze(pl, known, g[f"scan{i}.with_obs"].astype(np.float64), scanned)
+        assert np.array_equal(known, g[f"scan{i}.known"]), i
+        assert np.array_equal(scanned, g[f"scan{i}.scanned"]), i
+        assert len(seen) == 1 and np.array_equal(seen[0], known)
+
+
 def test_mppi_controller_tracks_reference_path(mazes):
     from ditreeonlineplanner_b200.mppi import MPPI
     grid = mazes["boxes"]

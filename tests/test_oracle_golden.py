@@ -220,3 +220,22 @@ def test_probmap_oracle(mazes):
         blend = orc.combine_log_blend(g[f"{str(g[f'{i}.maze'])}.prior"], g[f"{i}.pdf"])
         np.testing.assert_allclose(blend, g[f"{i}.blend"], rtol=1e-13, atol=1e-300)
         assert np.array_equal(orc.sample_cells(g[f"{i}.blend"], g[f"{i}.u"]), g[f"{i}.idx"])
+
+
+def test_online_path_check_and_scan_writeback(mazes):
+    """check_no_obstacles_in_path / scan_and_update_maze (run_scenarios_with_lidar_DiTree.py:112-127,158-181):
+    golden = the reference functions' own source exec'ed on seeded inputs (tools/gen_golden.py::gen_online)."""
+    g = golden("online.npz")
+    hits = 0
+    for i in range(int(g["n_path"])):
+        want = int(g[f"path{i}.idx"])
+        got = orc.path_first_obstacle(g[f"path{i}.path"], g[f"path{i}.scanned"].astype(np.float64))
+        assert got == want, i
+        hits += want >= 0
+    assert 10 < hits < int(g["n_path"])        # both outcomes are exercised
+    for i in range(int(g["n_scan"])):
+        base = mazes["boxes"].astype(np.float64)
+        known, scanned = base.copy(), np.zeros_like(base)
+        orc.scan_and_update_maze(g[f"scan{i}.state"], known, g[f"scan{i}.with_obs"].astype(np.float64), scanned)
+        assert np.array_equal(known, g[f"scan{i}.known"]), i
+        assert np.array_equal(scanned, g[f"scan{i}.scanned"]), i

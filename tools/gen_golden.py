@@ -329,8 +329,12 @@ def gen_cond():
     save("cond.npz", **out)
 
 
-def gen_denoiser():
-    for tag, dims, B, K, seed in (("small", [64, 128, 256], 3, 3, 11), ("large", [512, 1024, 2048], 1, 1, 12)):
+def gen_denoiser(cases=None):
+    """`large_b64_k{1,10}`: SURVEY 8(c) item 7 -- the reference DiffusionSampler.forward of the `large` net at
+    B = 64 (whole samples fill the GEMM tiles: the fused-GroupNorm CTA-pair kernels, not the split-K path)."""
+    cases = cases or (("small", [64, 128, 256], 3, 3, 11), ("large", [512, 1024, 2048], 1, 1, 12),
+                      ("large_b64_k1", [512, 1024, 2048], 64, 1, 13), ("large_b64_k10", [512, 1024, 2048], 64, 10, 14))
+    for tag, dims, B, K, seed in cases:
         sd = denoiser_ref.init_params(seed=seed, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims)
         net = ConditionalUnet1DWithLocalMap(input_dim=2, encoder_name="resnet", embedding_dim=400,
                                             additional_global_cond_dim=7, local_map_size=20, down_dims=dims)
@@ -341,6 +345,7 @@ def gen_denoiser():
         cond = torch.randn(B, 7, generator=g) * 0.5
         sample = torch.randn(B, 64, 2, generator=g)
         ts = torch.full((B,), 6.7166)
+        torch.set_num_threads(os.cpu_count() or 1)
         with torch.no_grad():
             enc = net.encoder(lm01 * 2 - 1)
             vel = net(sample=sample, local_map=lm01 * 2 - 1, timestep=ts, global_cond=cond)
@@ -421,6 +426,79 @@ class _FakeClock:
     def time(self):
         self.t += self.step
         return self.t
+
+
+def _reference_functions(path, names):
+    """The named top-level functions of a reference script whose module cannot be imported here (it imports
+    absent packages at module level): their source segments are exec'ed unmodified, with NumPy and a stub
+    `plt` as their globals."""
+    import ast
+    import types
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "plt": types.SimpleNamespace()}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def gen_online():
+    """check_no_obstacles_in_path / scan_and_update_maze (run_scenarios_with_lidar_DiTree.py:112-127,158-181)
+    run from their own source on seeded paths, scanned maps and poses."""
+    check_path, scan_update = _reference_functions(os.path.join(REF, "run_scenarios_with_lidar_DiTree.py"),
+                                                   ["check_no_obstacles_in_path", "scan_and_update_maze"])
+    import types
+    rng = np.random.default_rng(1212)
+    out = {}
+    n_cases = 0
+    for m in ("boxes", "random_large", "shapes", "val_maze_10"):
+        maze = load_maze(m)
+        R, C = maze.shape
+        env = car_env.CarEnv(maze_map=maze.copy(), collision_checking=False)
+        planner = types.SimpleNamespace(env=env)
+        for _ in range(12):
+            scanned = rng.choice([0.0, 1.0, 2.0], size=maze.shape, p=[0.55, 0.2, 0.25])
+            n = int(rng.integers(1, 60))
+            # a smooth-ish path inside the map (points outside would index from the end, like NumPy does)
+            p0 = np.array([rng.uniform(-C / 2 + 0.6, C / 2 - 0.6), rng.uniform(-R / 2 + 0.6, R / 2 - 0.6)])
+            steps = rng.normal(0, 0.25, (n, 2)).cumsum(0)
+            xy = np.clip(p0 + steps, [-C / 2 + 0.01, -R / 2 + 0.01], [C / 2 - 0.01, R / 2 - 0.01])
+            path = np.concatenate([xy, rng.normal(0, 1, (n, 4))], 1).astype(np.float32).astype(np.float64)
+            if n_cases % 5 == 4:   # some clear paths
+                scanned[scanned == 1] = 2
+            out[f"path{n_cases}.maze"] = np.array(MAZES.index(m))
+            out[f"path{n_cases}.scanned"] = scanned.astype(np.uint8)
+            out[f"path{n_cases}.path"] = path
+            out[f"path{n_cases}.idx"] = np.array(check_path(planner, scanned, path))
+            n_cases += 1
+    out["n_path"] = np.array(n_cases)
+    # scan_and_update_maze: lidar scan from the car's state, write-back into the known map and the scanned map
+    maze = load_maze("boxes")
+    n_scan = 0
+    for (r0, c0, h, w) in ((10, 15, 1, 4), (9, 16, 2, 2), (7, 16, 2, 3), (1, 7, 4, 4)):
+        with_obs = insert_box(maze, r0, c0, h, w)
+        free = np.argwhere(with_obs == 0)
+        for _ in range(3):
+            env = car_env.CarEnv(maze_map=maze.copy(), collision_checking=False)
+            env.lidar2dsim = Lidar2DSim(noise_std=0.0)
+            cell = free[rng.integers(len(free))]
+            xy = env.cell_rowcol_to_xy(cell) + rng.uniform(-0.3, 0.3, 2)
+            st = np.array([xy[0], xy[1], rng.uniform(-np.pi, np.pi), 1.0, 0.5, 0.0]).astype(np.float32).astype(np.float64)
+            env.set_state(st.copy())
+            known = maze.copy()
+            scanned = np.zeros_like(maze)
+            updates = []
+            planner = types.SimpleNamespace(env=env, update_maze=lambda mz: updates.append(mz.copy()))
+            scan_update(planner, known, with_obs, scanned)
+            out[f"scan{n_scan}.state"] = st
+            out[f"scan{n_scan}.with_obs"] = with_obs.astype(np.uint8)
+            out[f"scan{n_scan}.known"] = known.astype(np.uint8)
+            out[f"scan{n_scan}.scanned"] = scanned.astype(np.uint8)
+            assert len(updates) == 1 and np.array_equal(updates[0], known)
+            n_scan += 1
+    out["n_scan"] = np.array(n_scan)
+    save("online.npz", **out)
 
 
 def gen_tree():
@@ -605,10 +683,13 @@ def gen_probmap():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["data", "schedule", "local_map", "collide_car", "collide_ant", "bicycle", "propagate",
-                             "cond", "denoiser", "lidar", "probe", "tree", "tree_scenarios", "probmap"]
+                             "cond", "denoiser", "lidar", "probe", "online", "tree", "tree_scenarios", "probmap"]
     fns = dict(data=gen_data_fixtures, schedule=gen_schedule, local_map=gen_local_map, collide_car=gen_collide_car,
                collide_ant=gen_collide_ant, bicycle=gen_bicycle, propagate=gen_propagate, cond=gen_cond,
-               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, tree=gen_tree, tree_scenarios=gen_tree_scenarios, probmap=gen_probmap)
+               denoiser=gen_denoiser, lidar=gen_lidar, probe=gen_probe, online=gen_online, tree=gen_tree, tree_scenarios=gen_tree_scenarios, probmap=gen_probmap)
+    # only the batched large-net cases (minutes of torch-CPU time), leaving the committed small ones untouched
+    fns["denoiser_batch"] = lambda: gen_denoiser(cases=(("large_b64_k1", [512, 1024, 2048], 64, 1, 13),
+                                                        ("large_b64_k10", [512, 1024, 2048], 64, 10, 14)))
     for w in which:
         print(f"[{w}]")
         fns[w]()

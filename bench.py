@@ -183,7 +183,8 @@ def parity_check(args, grid, meta, sd, st_np, prev_np, noise, res, n_check=32):
     lm = orc.local_map(grid, s64[:, 0], s64[:, 1], s64[:, 2], 20, 0.2, 1.0, (C / 2, R / 2))
     cond = orc.build_cond_car(s64, prev_np[idx].astype(np.float64), goal, meta, 20.0)
     torch.set_num_threads(os.cpu_count() or 1)
-    want = dref.fm_sample(sd, noise[idx].cpu(), torch.from_numpy(cond), torch.from_numpy(lm), args.ode_steps)
+    want = dref.fm_sample(sd, noise[idx].cpu(), torch.from_numpy(cond), torch.from_numpy(lm), args.ode_steps, None, None,
+                           return_normalised=True).numpy().astype(np.float64)
     didx = torch.as_tensor(idx, device=res["actions"].device)
     got_act = res["actions"][didx].cpu().numpy().astype(np.float64)
     got = (got_act - meta["Actions_mean"]) / meta["Actions_std"]

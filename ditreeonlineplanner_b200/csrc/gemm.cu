@@ -200,6 +200,61 @@ __device__ __forceinline__ float mish_f(float x) {
   return x * (n * inv);
 }
 
+// ---- packed fp32 (f32x2) arithmetic: one FFMA2 / FMUL2 / FADD2 does two lanes' worth of work per issue slot and
+// per pass through the fma pipe, which is what bounds the fused epilogue (3-register FFMA: one warp instruction
+// per two cycles per scheduler).  A u64 holds columns (j, j + 1): element j in the low half, as two consecutive
+// floats loaded from memory do.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 pk2u(uint32_t lo, uint32_t hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// mish on a pair: x * n / (n + 2) with n = e (e + 2), e = exp(x), written as x * (1 - 2 / (e (e + 2) + 2)): no
+// clamp is needed (e = inf gives 1 / inf = 0, hence x; e = 0 gives 1 - 2 / 2 = 0) and the pair costs 5 packed
+// operations + 4 MUFU instead of 2 x 9.  The subtraction loses RELATIVE accuracy only where mish itself is below
+// 1e-5 in magnitude (x < -12): absolute error < 3e-7 everywhere, far below the bf16 output's resolution.
+__device__ __forceinline__ u64 mish2(u64 x) {
+  float a0, a1, e0, e1, d0, d1, r0, r1;
+  upk2(fmul2(x, pk2(1.4426950408889634f, 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const u64 e = pk2(e0, e1);
+  upk2(ffma2(e, fadd2(e, pk2(2.0f, 2.0f)), pk2(2.0f, 2.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return fmul2(x, ffma2(pk2(r0, r1), pk2(-2.0f, -2.0f), pk2(1.0f, 1.0f)));
+}
+// two consecutive packed pairs (four floats) from shared memory in one LDS.128
+__device__ __forceinline__ void lds4(const float* p, u64& a, u64& b) {
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  a = v.x;
+  b = v.y;
+}
+
 template <int NG>
 __device__ __forceinline__ float pick(const float (&a)[NG], int i) {
   float r = a[0];
@@ -512,8 +567,9 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const int smp_in_tile = g.tiles_per_sample > 0 ? 0 : row / g.T;
       if (EPI == EPI_GN_MISH) {
         float gs[NLG], gq[NLG];
+        u64 gs2[NLG], gq2[NLG];   // (even column, odd column) partial sums, folded after the loop
 #pragma unroll
-        for (int i = 0; i < NLG; ++i) gs[i] = gq[i] = 0.f;
+        for (int i = 0; i < NLG; ++i) gs2[i] = gq2[i] = 0ull;
         // pass 1: per-row partial sums of (acc + bias) and its square for the groups of this slice
         tmem_ld16(taddr, rb[0]);
 #pragma unroll
@@ -522,15 +578,24 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           if (c + 1 < NCH) tmem_ld16(taddr + (c + 1) * CH, rb[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < CH; j += 4) {
-            const float4 bi = *reinterpret_cast<const float4*>(sp + c * CH + j);
-            const float bia[4] = {bi.x, bi.y, bi.z, bi.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v = __uint_as_float(rb[c & 1][j + e]) + bia[e];
-              gs[(GW <= HALF) ? (c * CH + j + e) / GW : 0] += v;
-              gq[(GW <= HALF) ? (c * CH + j + e) / GW : 0] += v * v;
-            }
+            u64 b01, b23;
+            lds4(sp + c * CH + j, b01, b23);
+            const u64 v01 = fadd2(pk2u(rb[c & 1][j], rb[c & 1][j + 1]), b01);
+            const u64 v23 = fadd2(pk2u(rb[c & 1][j + 2], rb[c & 1][j + 3]), b23);
+            const int u = (GW <= HALF) ? (c * CH + j) / GW : 0;   // GW >= 8: the four columns share a group
+            gs2[u] = fadd2(gs2[u], v01);
+            gq2[u] = ffma2(v01, v01, gq2[u]);
+            gs2[u] = fadd2(gs2[u], v23);
+            gq2[u] = ffma2(v23, v23, gq2[u]);
           }
+        }
+#pragma unroll
+        for (int i = 0; i < NLG; ++i) {
+          float lo, hi;
+          upk2(gs2[i], lo, hi);
+          gs[i] = lo + hi;
+          upk2(gq2[i], lo, hi);
+          gq[i] = lo + hi;
         }
         // reduce over the rows of this sample held by this warp (segments of min(T,32) lanes) ...
         const int span = g.T < 32 ? g.T : 32;
@@ -632,65 +697,59 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         }
         const uint32_t* r = rb[c & 1];
-        float y[CH];
+        u64 y2[CH / 2];   // y2[i] = columns (c0 + 2 i, c0 + 2 i + 1)
         if (EPI == EPI_GN_MISH) {
           if (coef_smem) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              const float4 A4 = *reinterpret_cast<const float4*>(cf + c0 + j);
-              const float4 B4 = *reinterpret_cast<const float4*>(cf + BN + c0 + j);
-              y[j + 0] = mish_f(fmaf(__uint_as_float(r[j + 0]), A4.x, B4.x));
-              y[j + 1] = mish_f(fmaf(__uint_as_float(r[j + 1]), A4.y, B4.y));
-              y[j + 2] = mish_f(fmaf(__uint_as_float(r[j + 2]), A4.z, B4.z));
-              y[j + 3] = mish_f(fmaf(__uint_as_float(r[j + 3]), A4.w, B4.w));
+              u64 A01, A23, B01, B23;
+              lds4(cf + c0 + j, A01, A23);
+              lds4(cf + BN + c0 + j, B01, B23);
+              y2[j / 2] = mish2(ffma2(pk2u(r[j], r[j + 1]), A01, B01));
+              y2[j / 2 + 1] = mish2(ffma2(pk2u(r[j + 2], r[j + 3]), A23, B23));
             }
           } else {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
-              const float4 ga = *reinterpret_cast<const float4*>(sp + BN + c0 + j);
-              const float4 be = *reinterpret_cast<const float4*>(sp + 2 * BN + c0 + j);
-              const float bia[4] = {bi.x, bi.y, bi.z, bi.w}, gam[4] = {ga.x, ga.y, ga.z, ga.w},
-                          bet[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int u = (GW <= HALF) ? (c0 + j + e) / GW : 0;
-                const float v = __uint_as_float(r[j + e]) + bia[e];
-                y[j + e] = mish_f((v - mean[u]) * rstd[u] * gam[e] + bet[e]);
-              }
+              u64 b01, b23, g01, g23, e01, e23;
+              lds4(sp + c0 + j, b01, b23);
+              lds4(sp + BN + c0 + j, g01, g23);
+              lds4(sp + 2 * BN + c0 + j, e01, e23);
+              const int u = (GW <= HALF) ? (c0 + j) / GW : 0;   // GW >= 8: the four columns share a group
+              const u64 rs = pk2(rstd[u], rstd[u]), nm = pk2(-mean[u] * rstd[u], -mean[u] * rstd[u]);
+              // ((acc + bias) - mean) * rstd * gamma + beta
+              y2[j / 2] = mish2(ffma2(ffma2(fadd2(pk2u(r[j], r[j + 1]), b01), rs, nm), g01, e01));
+              y2[j / 2 + 1] = mish2(ffma2(ffma2(fadd2(pk2u(r[j + 2], r[j + 3]), b23), rs, nm), g23, e23));
             }
           }
           if (film_smem) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              const float4 sc = *reinterpret_cast<const float4*>(fs + c0 + j);
-              const float4 sh = *reinterpret_cast<const float4*>(fs + BN + c0 + j);
-              y[j + 0] = fmaf(y[j + 0], sc.x, sh.x);
-              y[j + 1] = fmaf(y[j + 1], sc.y, sh.y);
-              y[j + 2] = fmaf(y[j + 2], sc.z, sh.z);
-              y[j + 3] = fmaf(y[j + 3], sc.w, sh.w);
+              u64 sc01, sc23, sh01, sh23;
+              lds4(fs + c0 + j, sc01, sc23);
+              lds4(fs + BN + c0 + j, sh01, sh23);
+              y2[j / 2] = ffma2(y2[j / 2], sc01, sh01);
+              y2[j / 2 + 1] = ffma2(y2[j / 2 + 1], sc23, sh23);
             }
           } else if (film_row) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(film_row + c0 + j));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(film_row + g.N + c0 + j));
-              const float4 ts = *reinterpret_cast<const float4*>(sp + 3 * BN + c0 + j);
-              const float4 tb = *reinterpret_cast<const float4*>(sp + 4 * BN + c0 + j);
-              y[j + 0] = y[j + 0] * (sc.x + ts.x) + (sh.x + tb.x);
-              y[j + 1] = y[j + 1] * (sc.y + ts.y) + (sh.y + tb.y);
-              y[j + 2] = y[j + 2] * (sc.z + ts.z) + (sh.z + tb.z);
-              y[j + 3] = y[j + 3] * (sc.w + ts.w) + (sh.w + tb.w);
+              const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2*>(film_row + c0 + j));
+              const ulonglong2 sh = __ldg(reinterpret_cast<const ulonglong2*>(film_row + g.N + c0 + j));
+              u64 ts01, ts23, tb01, tb23;
+              lds4(sp + 3 * BN + c0 + j, ts01, ts23);
+              lds4(sp + 4 * BN + c0 + j, tb01, tb23);
+              y2[j / 2] = ffma2(y2[j / 2], fadd2(sc.x, ts01), fadd2(sh.x, tb01));
+              y2[j / 2 + 1] = ffma2(y2[j / 2 + 1], fadd2(sc.y, ts23), fadd2(sh.y, tb23));
             }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < CH; j += 4) {
-            const float4 bi = *reinterpret_cast<const float4*>(sp + c0 + j);
-            y[j + 0] = __uint_as_float(r[j + 0]) + bi.x;
-            y[j + 1] = __uint_as_float(r[j + 1]) + bi.y;
-            y[j + 2] = __uint_as_float(r[j + 2]) + bi.z;
-            y[j + 3] = __uint_as_float(r[j + 3]) + bi.w;
+            u64 b01, b23;
+            lds4(sp + c0 + j, b01, b23);
+            y2[j / 2] = fadd2(pk2u(r[j], r[j + 1]), b01);
+            y2[j / 2 + 1] = fadd2(pk2u(r[j + 2], r[j + 3]), b23);
           }
         }
         if (res_row) {
@@ -699,12 +758,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             const uint4 pk = res_cur[j / 8];
             const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {  // bf16 -> fp32 is a 16-bit shift
-              y[j + 2 * u] += __uint_as_float(w4[u] << 16);
-              y[j + 2 * u + 1] += __uint_as_float(w4[u] & 0xFFFF0000u);
-            }
+            for (int u = 0; u < 4; ++u)  // bf16 -> fp32 is a 16-bit shift: word u holds columns (j + 2u, j + 2u + 1)
+              y2[j / 2 + u] = fadd2(y2[j / 2 + u], pk2u(w4[u] << 16, w4[u] & 0xFFFF0000u));
           }
         }
+        float y[CH];
+#pragma unroll
+        for (int i = 0; i < CH / 2; ++i) upk2(y2[i], y[2 * i], y[2 * i + 1]);
         if (EPI == EPI_PLAIN && g.relu) {
 #pragma unroll
           for (int j = 0; j < CH; ++j) y[j] = fmaxf(y[j], 0.f);

@@ -6,8 +6,9 @@ directory of Python scripts; it cannot be pip-installed and does not exist on th
 exactly the modules of the tree-expansion path (planners/base_planner.py:257-320 `propagate_action_sequence_env`,
 policies/fm_policy.py:53-212 `DiffusionSampler.forward`, car_env.py `CarEnv.step`, common/map_utils.py
 `create_local_map` / `is_colliding_car`, local_map_encoder.py + model/diffusion/* the network) and whatever they import
-from the reference tree into ``oracle/_ref/`` as sourceless ``.pyc`` files -- compiled outputs only, like a C reference's
-``.so``; no reference SOURCE is copied into the repository, and ``oracle/_ref/`` is git-ignored (it travels to the GPU
+from the reference tree into ``oracle/_ref/`` as marshalled code objects (``<module path>.code``, loaded by the
+finder in oracle/ref_arm.py; ``.pyc`` files do not survive the snapshot to the GPU box) -- compiled outputs only, like
+a C reference's ``.so``; no reference SOURCE is copied into the repository, and ``oracle/_ref/`` is git-ignored (it travels to the GPU
 box with the gpurun snapshot, like the built libditree.so).  ``oracle/_ref/metadata/carmaze.pt`` is re-created from the
 normaliser statistics the package already ships as a data fixture (ditreeonlineplanner_b200/data/metadata_carmaze.npz).
 
@@ -20,7 +21,7 @@ from __future__ import annotations
 
 import json
 import os
-import py_compile
+import marshal
 import shutil
 import subprocess
 import sys
@@ -68,9 +69,12 @@ def build(verbose=True):
     manifest = []
     for src in files:
         rel = os.path.relpath(src, ref_root)
-        dst = os.path.join(OUT, rel + "c")  # x.py -> x.pyc next to where the module lived: a sourceless import
+        dst = os.path.join(OUT, rel[:-3] + ".code")  # x.py -> x.code: marshal.dumps(compile(source))
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        py_compile.compile(src, cfile=dst, dfile="reference:" + rel, doraise=True, optimize=0)
+        with open(src, "rb") as f:
+            code = compile(f.read(), "reference:" + rel, "exec", dont_inherit=True, optimize=0)
+        with open(dst, "wb") as f:
+            f.write(marshal.dumps(code))
         manifest.append(rel)
     # the normaliser statistics the sampler loads relative to the CWD (policies/fm_policy.py:28-30)
     import numpy as np

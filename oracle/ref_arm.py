@@ -12,6 +12,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this mod
 from __future__ import annotations
 
 import contextlib
+import importlib.abc
+import importlib.util
+import marshal
 import os
 import sys
 
@@ -28,6 +31,41 @@ _PROTECTED = ("car_env", "common", "local_map_encoder", "planners", "policies", 
 
 def available():
     return os.path.isfile(os.path.join(REF_DIR, "MANIFEST.json"))
+
+
+class _CodeFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Imports `a.b` from oracle/_ref/a/b.code (a marshalled code object of the unmodified reference module, written
+    by oracle/build_ref.py with this same interpreter version); directories are namespace-style packages."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        base = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(base + ".code"):
+            return importlib.util.spec_from_loader(fullname, self, origin=base + ".code")
+        if os.path.isfile(os.path.join(base, "__init__.code")):
+            return importlib.util.spec_from_loader(fullname, self, origin=os.path.join(base, "__init__.code"), is_package=True)
+        if os.path.isdir(base) and fullname.split(".")[0] in _REF_TOP:
+            spec = importlib.util.spec_from_loader(fullname, self, origin=base, is_package=True)
+            spec.submodule_search_locations = [base]
+            return spec
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        origin = module.__spec__.origin
+        if os.path.isdir(origin):
+            return
+        module.__file__ = origin
+        with open(origin, "rb") as f:
+            code = marshal.loads(f.read())
+        exec(code, module.__dict__)
+
+
+_REF_TOP = ("common", "planners", "policies", "lidar_sim", "model")
 
 
 @contextlib.contextmanager
@@ -51,7 +89,8 @@ class Reference:
                  and not str(getattr(sys.modules[m], "__file__", None) or REF_DIR).startswith((REF_DIR, STUBS))]
         if clash:
             raise RuntimeError(f"oracle/ref_arm: modules {clash} are already imported from elsewhere")
-        sys.path[:0] = [STUBS, REF_DIR]
+        sys.path.insert(0, STUBS)
+        sys.meta_path.insert(0, _CodeFinder(REF_DIR))
         with _cwd(REF_DIR):
             import car_env
             import common.map_utils as map_utils
@@ -81,6 +120,11 @@ class Reference:
         goal = np.array([goal_xy[0], goal_xy[1], 0.0, 0.0, 0.0, 0.0])
         planner = self.RRT_Planner(start, goal, env_id="carmaze", environment=env, sampler=smp, action_horizon=S,
                                    local_map_size=20, local_map_scale=0.2, global_map_scale=1.0, time_budget=1)
+        # the reference picks 'cuda' whenever a GPU is visible (base_planner.py, fm_policy.py:26) and moves the sampler
+        # there; this arm is the reference's CPU path, so pin everything back to the host
+        planner.device = "cpu"
+        smp.to("cpu")
+        smp.device = "cpu"
         mu = self.map_utils
 
         def run(states, prev_actions, seed=None):

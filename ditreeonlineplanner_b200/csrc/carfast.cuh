@@ -42,20 +42,30 @@ struct QMapView {
   float eps;
 };
 
-static inline QMapView dt_qmap_view(const dt_ctx* ctx) {
+static inline QMapView dt_qmap_view_of(const uint32_t* d_qmap, int qmap_bytes, int rows, int cols) {
   QMapView q;
-  q.g = ctx->qmap_bytes ? ctx->d_qmap : nullptr;
-  q.bytes = ctx->qmap_bytes;
-  q.pitch = ctx->cols + 2 * DT_QPAD + 1;
+  q.g = qmap_bytes ? d_qmap : nullptr;
+  q.bytes = qmap_bytes;
+  q.pitch = cols + 2 * DT_QPAD + 1;
   q.bias = (int)(0u - 0x4B400000u * (unsigned)(q.pitch + 1));
-  q.cxp = 0.5f * (float)ctx->cols + (float)DT_QPAD;
-  q.cyp = 0.5f * (float)ctx->rows + (float)DT_QPAD;
-  q.wmax = (float)(ctx->cols + 2 * DT_QPAD) - 0.5f;
-  q.umax = (float)(ctx->rows + 2 * DT_QPAD) - 0.5f;
-  const int mx = ctx->rows > ctx->cols ? ctx->rows : ctx->cols;
+  q.cxp = 0.5f * (float)cols + (float)DT_QPAD;
+  q.cyp = 0.5f * (float)rows + (float)DT_QPAD;
+  q.wmax = (float)(cols + 2 * DT_QPAD) - 0.5f;
+  q.umax = (float)(rows + 2 * DT_QPAD) - 0.5f;
+  const int mx = rows > cols ? rows : cols;
   q.eps = 1.1920929e-7f * ((float)mx + 4.0f) + 0.075f * DT_SC_ERR + 1.0e-7f;
   return q;
 }
+
+static inline QMapView dt_qmap_view(const dt_ctx* ctx) {
+  return dt_qmap_view_of(ctx->d_qmap, ctx->qmap_bytes, ctx->rows, ctx->cols);
+}
+
+// one staged map slot as the kernels see it (dt_ctx::d_map_table)
+struct MapEntry {
+  MapView m;
+  QMapView q;
+};
 
 #ifdef __CUDACC__
 // Stage the occupancy grid and the quadrant table with two bulk TMA copies on one mbarrier.

@@ -17,6 +17,18 @@
 
 struct dt_denoiser;  // denoiser.cu
 
+// Additional occupancy grids staged next to the main one (dt_set_map_slot): the device-resident planner runs
+// several scenarios -- on different mazes -- in ONE device pass, a block of candidates per scenario, and every
+// block stages the grid of its scenario (a per-group map index resolved through a device table of views).
+#define DT_MAX_MAP_SLOTS 32
+struct dt_map_slot {
+  uint8_t* d_map = nullptr;
+  uint32_t* d_qmap = nullptr;
+  int rows = 0, cols = 0, map_bytes = 0, qmap_bytes = 0;
+  size_t map_cap = 0, qmap_cap = 0;
+  double s_global = 1.0;
+};
+
 struct dt_ctx {
   int device = 0;
   std::string err;
@@ -31,6 +43,9 @@ struct dt_ctx {
   uint32_t* d_qmap = nullptr;
   int qmap_bytes = 0;
   size_t map_capacity = 0, qmap_capacity = 0;
+  dt_map_slot slots[DT_MAX_MAP_SLOTS];
+  void* d_map_table = nullptr;        // MapEntry[DT_MAX_MAP_SLOTS] (carfast.cuh), the views of the staged slots
+  int slots_max_bytes = 0;            // max over slots of map_bytes + qmap_bytes (dynamic shared memory of a block)
   bool prop_attr_set = false;  // dynamic shared memory opt-in of the propagate kernels done on this device
   // device-side status word (DT_E_*), plus small scratch for reductions
   int* d_status = nullptr;

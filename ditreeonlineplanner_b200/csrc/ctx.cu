@@ -1,5 +1,5 @@
 // ctx.cu -- context lifetime, map upload, status word.
-#include "common.cuh"
+#include "carfast.cuh"
 
 void dt_denoiser_free(dt_ctx* ctx);         // denoiser.cu
 void dt_denoiser_drop_graphs(dt_ctx* ctx);  // denoiser.cu
@@ -40,6 +40,11 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   dt_denoiser_free(ctx);
   if (ctx->d_map) cudaFree(ctx->d_map);
   if (ctx->d_qmap) cudaFree(ctx->d_qmap);
+  for (dt_map_slot& sl : ctx->slots) {
+    if (sl.d_map) cudaFree(sl.d_map);
+    if (sl.d_qmap) cudaFree(sl.d_qmap);
+  }
+  if (ctx->d_map_table) cudaFree(ctx->d_map_table);
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -131,13 +136,12 @@ int dt_ensure_scratch(dt_ctx* ctx, size_t bytes) {
   return DT_OK;
 }
 
-extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int cols, float s_global, void* stream) {
-  if (!ctx) return DT_E_ARG;
-  if (!grid_host || rows < 1 || cols < 1 || (int64_t)rows * cols > DT_MAX_MAP_CELLS || !(s_global > 0.f))
-    return dt_fail(ctx, DT_E_ARG, "dt_set_map: bad grid (1 <= rows*cols <= 16384, s_global > 0)");
-  DT_CUDA(cudaSetDevice(ctx->device));
-  const int padded = ((rows * cols + 15) / 16) * 16;
-  std::vector<uint8_t> bytes(padded, 0);
+// Host-side form of a grid: bytes (1 = wall, 2 = other non-zero, 0 = free; padded to 16) and the quadrant table of
+// the car collision fast path.
+static void dt_build_map_host(const float* grid_host, int rows, int cols, std::vector<uint8_t>& bytes,
+                              std::vector<uint32_t>& q, int& padded, int& qpadded) {
+  padded = ((rows * cols + 15) / 16) * 16;
+  bytes.assign(padded, 0);
   for (int i = 0; i < rows * cols; ++i) bytes[i] = (grid_host[i] == 1.0f) ? 1 : (grid_host[i] != 0.0f ? 2 : 0);
   // Quadrant table of the car collision fast path (carfast.cuh).  The grid is padded by DT_QPAD rings of
   // "always collides" cells (a ball centre outside the grid collides, common/map_utils.py:255-259) and the
@@ -154,8 +158,8 @@ extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int col
   // Built only when rows <= cols (on taller maps the row-count clip can index past the last column: NumPy
   // raises IndexError, and the exact code, which reports that, is used instead) and when it fits in
   // DT_QMAP_MAX_BYTES of shared memory.
-  std::vector<uint32_t> q;
-  int qpadded = 0;
+  q.clear();
+  qpadded = 0;
   const int VR = rows + 2 * DT_QPAD + 1, VC = cols + 2 * DT_QPAD + 1;
   if (rows <= cols && (size_t)VR * VC * 16 <= DT_QMAP_MAX_BYTES) {
     qpadded = VR * VC * 16;
@@ -177,6 +181,17 @@ extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int col
             q[((size_t)k * VC + j) * 4 + 2 * a + b] = w;
           }
   }
+}
+
+extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int cols, float s_global, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!grid_host || rows < 1 || cols < 1 || (int64_t)rows * cols > DT_MAX_MAP_CELLS || !(s_global > 0.f))
+    return dt_fail(ctx, DT_E_ARG, "dt_set_map: bad grid (1 <= rows*cols <= 16384, s_global > 0)");
+  DT_CUDA(cudaSetDevice(ctx->device));
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> q;
+  int padded = 0, qpadded = 0;
+  dt_build_map_host(grid_host, rows, cols, bytes, q, padded, qpadded);
   cudaStream_t st = (cudaStream_t)stream;
   if ((size_t)padded > ctx->map_capacity || (size_t)qpadded > ctx->qmap_capacity) {
     DT_CUDA(cudaStreamSynchronize(st));
@@ -204,6 +219,48 @@ extern "C" int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int col
   ctx->cols = cols;
   ctx->s_global = (double)s_global;
   ctx->map_bytes = padded;
+  return DT_OK;
+}
+
+extern "C" int dt_set_map_slot(dt_ctx* ctx, int slot, const float* grid_host, int rows, int cols, float s_global,
+                               void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (slot < 0 || slot >= DT_MAX_MAP_SLOTS) return dt_fail(ctx, DT_E_ARG, "dt_set_map_slot: slot out of range (0..31)");
+  if (!grid_host || rows < 1 || cols < 1 || (int64_t)rows * cols > DT_MAX_MAP_CELLS || !(s_global > 0.f))
+    return dt_fail(ctx, DT_E_ARG, "dt_set_map_slot: bad grid (1 <= rows*cols <= 16384, s_global > 0)");
+  DT_CUDA(cudaSetDevice(ctx->device));
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> q;
+  int padded = 0, qpadded = 0;
+  dt_build_map_host(grid_host, rows, cols, bytes, q, padded, qpadded);
+  cudaStream_t st = (cudaStream_t)stream;
+  dt_map_slot& s = ctx->slots[slot];
+  DT_CUDA(cudaStreamSynchronize(st));  // a pass still reading the old contents of this slot must have drained
+  if ((size_t)padded > s.map_cap) {
+    if (s.d_map) DT_CUDA(cudaFree(s.d_map));
+    s.d_map = nullptr; s.map_cap = 0;
+    DT_CUDA(cudaMalloc(&s.d_map, padded));
+    s.map_cap = padded;
+  }
+  if ((size_t)qpadded > s.qmap_cap) {
+    if (s.d_qmap) DT_CUDA(cudaFree(s.d_qmap));
+    s.d_qmap = nullptr; s.qmap_cap = 0;
+    DT_CUDA(cudaMalloc(&s.d_qmap, qpadded));
+    s.qmap_cap = qpadded;
+  }
+  if (!ctx->d_map_table) {
+    DT_CUDA(cudaMalloc(&ctx->d_map_table, sizeof(MapEntry) * DT_MAX_MAP_SLOTS));
+    DT_CUDA(cudaMemset(ctx->d_map_table, 0, sizeof(MapEntry) * DT_MAX_MAP_SLOTS));
+  }
+  DT_CUDA(cudaMemcpyAsync(s.d_map, bytes.data(), padded, cudaMemcpyHostToDevice, st));
+  if (qpadded) DT_CUDA(cudaMemcpyAsync(s.d_qmap, q.data(), qpadded, cudaMemcpyHostToDevice, st));
+  s.rows = rows; s.cols = cols; s.map_bytes = padded; s.qmap_bytes = qpadded; s.s_global = (double)s_global;
+  MapEntry e;
+  e.m.g = s.d_map; e.m.rows = rows; e.m.cols = cols; e.m.bytes = padded; e.m.s = (double)s_global;
+  e.q = dt_qmap_view_of(s.d_qmap, qpadded, rows, cols);
+  DT_CUDA(cudaMemcpyAsync((MapEntry*)ctx->d_map_table + slot, &e, sizeof e, cudaMemcpyHostToDevice, st));
+  DT_CUDA(cudaStreamSynchronize(st));  // the staging vectors and `e` die at return
+  if (padded + qpadded > ctx->slots_max_bytes) ctx->slots_max_bytes = padded + qpadded;
   return DT_OK;
 }
 

@@ -26,6 +26,24 @@ class ModelCfg(C.Structure):
                 ("map_size", C.c_int), ("down_dims", C.c_int * 3), ("max_batch", C.c_int)]
 
 
+class PlanCfg(C.Structure):
+    _fields_ = [("unit_slots", C.c_int32), ("edge_slots", C.c_int32), ("node_cap", C.c_int32), ("action_horizon", C.c_int32),
+                ("n_sched", C.c_int32), ("sched_chunks", C.c_int32 * 8), ("iteration_cap", C.c_int32),
+                ("ode_steps", C.c_int32), ("max_units", C.c_int32), ("max_path", C.c_int32),
+                ("goal_sample_rate", C.c_float), ("goal_conditioning_bias", C.c_float),
+                ("local_map_scale", C.c_double), ("norm", C.c_double * 16)]
+
+
+class PlanUnit(C.Structure):
+    _fields_ = [("start", C.c_float * 6), ("goal", C.c_float * 2), ("half_w", C.c_float), ("half_h", C.c_float),
+                ("map_slot", C.c_int32), ("seed", C.c_uint32), ("unit_id", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("unit_id", "goal_reached", "has_path", "n_states", "n_actions", "n_nodes",
+                                         "iterations", "first_pass", "last_pass", "collisions", "chunks", "error")]
+
+
 # name -> (restype, argtypes); every symbol include/ditree.h declares
 SIGNATURES = {
     "dt_ctx_create": (C.c_int, [C.c_int, C.POINTER(c_p)]),
@@ -34,6 +52,15 @@ SIGNATURES = {
     "dt_version": (C.c_char_p, []),
     "dt_set_option": (C.c_int, [c_p, C.c_char_p, C.c_int]),
     "dt_set_map": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_float, c_p]),
+    "dt_set_map_slot": (C.c_int, [c_p, C.c_int, c_p, C.c_int, C.c_int, C.c_float, c_p]),
+    "dt_local_map_slots": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, C.c_int, C.c_double, c_p, C.c_int, c_p, c_p]),
+    "dt_plan_create": (C.c_int, [c_p, C.POINTER(PlanCfg), C.POINTER(c_p)]),
+    "dt_plan_destroy": (None, [c_p]),
+    "dt_plan_push": (C.c_int, [c_p, C.POINTER(PlanUnit), C.c_int, c_p]),
+    "dt_plan_pass": (C.c_int, [c_p, c_p]),
+    "dt_plan_counters": (C.c_int, [c_p, c_i64, C.c_int, C.POINTER(C.c_int32)]),
+    "dt_plan_fetch": (C.c_int, [c_p, C.c_int, C.POINTER(PlanResult), c_p, c_p, C.c_int, c_p]),
+    "dt_plan_peek_tree": (C.c_int, [c_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_p, c_p, C.c_int, c_p]),
     "dt_collide_car": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "dt_collide_points": (C.c_int, [c_p, c_p, c_p, c_i64, c_i64, C.c_double, C.c_double, c_p, c_p]),
     "dt_collide_ant": (C.c_int, [c_p, c_p, c_i64, c_i64, C.c_double, c_p, c_p]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libditree.so")
 STAMP = os.path.join(HERE, ".libditree.stamp")
-SOURCES = ["ctx.cu", "geom.cu", "propagate.cu", "reduce.cu", "probmap.cu", "cond.cu", "gemm.cu", "denoiser.cu"]
+SOURCES = ["ctx.cu", "geom.cu", "propagate.cu", "reduce.cu", "probmap.cu", "cond.cu", "gemm.cu", "denoiser.cu", "planner.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "--expt-relaxed-constexpr"]
 

@@ -92,6 +92,7 @@ static inline int dt_fail_cuda(dt_ctx* ctx, cudaError_t e, const char* where) {
   } while (0)
 
 int dt_ensure_scratch(dt_ctx* ctx, size_t bytes);
+dt_model_cfg dt_denoiser_cfg(dt_ctx* ctx);  // denoiser.cu: configuration of the loaded denoiser (ctx->den != nullptr)
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

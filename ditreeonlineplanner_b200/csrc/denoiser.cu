@@ -1120,6 +1120,8 @@ static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, 
   return DT_OK;
 }
 
+dt_model_cfg dt_denoiser_cfg(dt_ctx* ctx) { return ctx->den->cfg; }
+
 #define NEED_MODEL()                                                            \
   if (!ctx) return DT_E_ARG;                                                    \
   if (!ctx->den) return dt_fail(ctx, DT_E_NOMODEL, "dt_load_denoiser has not been called")

@@ -255,6 +255,19 @@ __device__ __forceinline__ void lds4(const float* p, u64& a, u64& b) {
   b = v.y;
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one instruction per thread moves the 32 bytes -- a whole
+// sector -- a 16-column bf16 chunk of its row occupies, instead of two half-sector 128-bit ones
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 template <int NG>
 __device__ __forceinline__ float pick(const float (&a)[NG], int i) {
   float r = a[0];
@@ -262,6 +275,27 @@ __device__ __forceinline__ float pick(const float (&a)[NG], int i) {
   for (int k = 1; k < NG; ++k) r = (i == k) ? a[k] : r;
   return r;
 }
+
+#ifdef GEMM_TIMING
+// variant build only (tools/gemm_timing.py): cycle accounting of the roles, summed over the tiles of flagged launches
+//  [0] tiles seen by the MMA warp  [1] cycles waiting for a free accumulator  [2] main-loop cycles (issue to last commit)
+//  [3] tiles seen by epilogue warp 0  [4] cycles waiting for the accumulator  [5] pass 1  [6] statistics + coefficients
+//  [7] pass 2  [8] parameter staging + barriers before the wait  [9] kernel cycles (one CTA)  [10] CTAs
+__device__ unsigned long long g_gemm_dbg[16];
+extern "C" int dt_gemm_timing(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_gemm_dbg, sizeof(g_gemm_dbg));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_gemm_dbg, z, sizeof z);
+  }
+  return 0;
+}
+#define DBG_T(var) const long long var = clock64()
+#define DBG_ADD(i, v) atomicAdd(&g_gemm_dbg[i], (unsigned long long)(v))
+#else
+#define DBG_T(var)
+#define DBG_ADD(i, v)
+#endif
 
 struct GemmDev {
   int num_m_tiles, num_n_tiles, nseg, nkb_total;
@@ -286,6 +320,7 @@ struct GemmDev {
   // its partial sums slice_rows output rows further down (plain epilogue, fp32, reduced by k_splitk_epi)
   int ksplit, kb_per_slice;
   long long slice_rows;
+  int dbg;   // GEMM_TIMING builds: account this launch
 };
 
 template <int BN, int CG>
@@ -333,6 +368,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128, 256 or 512: powers of two >= 32
+  DBG_T(tk0);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P::kStages; ++s) {
@@ -430,8 +466,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       for (int tile = unit; tile < total_tiles; tile += n_units) {
         const int kb0_ = (tile % g.ksplit) * g.kb_per_slice;
         const int nkb = ((kb0_ + g.kb_per_slice < g.nkb_total) ? kb0_ + g.kb_per_slice : g.nkb_total) - kb0_;
+        DBG_T(tm0);
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tc_fence_after();
+        DBG_T(tm1);
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
@@ -460,6 +498,14 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             phase ^= 1;
           }
         }
+#ifdef GEMM_TIMING
+        if (g.dbg && lane == 0) {
+          const long long tm2 = clock64();
+          DBG_ADD(0, 1);
+          DBG_ADD(1, tm1 - tm0);
+          DBG_ADD(2, tm2 - tm1);
+        }
+#endif
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -552,6 +598,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         t = row % g.T;
       }
       const bool valid = (b < g.B) && (t < g.T);
+      DBG_T(te0);
       // publish this tile's (prefetched) parameters; the first barrier orders the previous tile's readers
       epi_bar_sync();
       if (et < BN) {
@@ -573,8 +620,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       }
       epi_bar_sync();
       if (tile + n_units < total_tiles) prefetch(tile + n_units);  // in flight during this tile
+      DBG_T(te1);
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      DBG_T(te2);
+#ifdef GEMM_TIMING
+      long long te3 = te2, te4 = te2;
+#endif
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
       const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off + slice * g.slice_rows;
       const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
@@ -618,6 +670,9 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           upk2(gq2[i], lo, hi);
           gq[i] = lo + hi;
         }
+#ifdef GEMM_TIMING
+        te3 = clock64();
+#endif
         // reduce over the rows of this sample held by this warp (segments of min(T,32) lanes) ...
         const int span = g.T < 32 ? g.T : 32;
 #pragma unroll
@@ -678,6 +733,9 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         epi_bar_sync();
       }
 
+#ifdef GEMM_TIMING
+      te4 = clock64();
+#endif
       // pass 2: normalise / activate / modulate and store this warp's slice of the columns
       const int nh = n0 + half * HALF;
       const float* film_row = (EPI == EPI_GN_MISH && g.film && valid && !film_smem) ? g.film + b * g.film_ld + nh : nullptr;
@@ -686,10 +744,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + nh : nullptr;
       __nv_bfloat16* out_b = g.out_bf16 ? g.out_bf16 + out_row * g.ldc + nh : nullptr;
       float* out_f = g.out_f32 ? g.out_f32 + out_row * g.ldc + nh : nullptr;
-      uint4 res_next[2];
+      // residual: 32 bytes (16 bf16 columns) per chunk, fetched RES_PF chunks ahead of their use
+      constexpr int RES_PF = 2;
+      uint32_t resq[RES_PF + 1][8];
       if (res_row) {
-        res_next[0] = __ldg(reinterpret_cast<const uint4*>(res_row));
-        res_next[1] = __ldg(reinterpret_cast<const uint4*>(res_row + 8));
+#pragma unroll
+        for (int d = 0; d < RES_PF; ++d)
+          if (d < NCH) ldg256(res_row + d * CH, resq[d]);
       }
       tmem_ld16(taddr, rb[0]);
 #pragma unroll
@@ -708,15 +769,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             else mbar_arrive_relaxed(bar_tempty + 8 * acc);
           }
         }
-        uint4 res_cur[2];
-        if (res_row) {  // software pipeline: this chunk's residual was requested one iteration ago
-          res_cur[0] = res_next[0];
-          res_cur[1] = res_next[1];
-          if (c + 1 < NCH) {
-            res_next[0] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + CH));
-            res_next[1] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + CH + 8));
-          }
-        }
+        if (res_row && c + RES_PF < NCH) ldg256(res_row + c0 + RES_PF * CH, resq[(c + RES_PF) % (RES_PF + 1)]);
         const uint32_t* r = rb[c & 1];
         u64 y2[CH / 2];   // y2[i] = columns (c0 + 2 i, c0 + 2 i + 1)
         if (EPI == EPI_GN_MISH) {
@@ -774,14 +827,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         }
         if (res_row) {
+          const uint32_t* w8 = resq[c % (RES_PF + 1)];
 #pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            const uint4 pk = res_cur[j / 8];
-            const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)  // bf16 -> fp32 is a 16-bit shift: word u holds columns (j + 2u, j + 2u + 1)
-              y2[j / 2 + u] = fadd2(y2[j / 2 + u], pk2u(w4[u] << 16, w4[u] & 0xFFFF0000u));
-          }
+          for (int u = 0; u < CH / 2; ++u)  // bf16 -> fp32 is a 16-bit shift: word u holds columns (2u, 2u + 1)
+            y2[u] = fadd2(y2[u], pk2u(w8[u] << 16, w8[u] & 0xFFFF0000u));
         }
         float y[CH];
 #pragma unroll
@@ -792,14 +841,13 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         }
         if (valid) {
           if (out_b) {
+            uint32_t pk[CH / 2];
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              uint4 pk;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) h2[u] = __floats2bfloat162_rn(y[j + 2 * u], y[j + 2 * u + 1]);
-              *reinterpret_cast<uint4*>(out_b + c0 + j) = pk;
+            for (int u = 0; u < CH / 2; ++u) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * u], y[2 * u + 1]);
+              pk[u] = *reinterpret_cast<const uint32_t*>(&h2);
             }
+            stg256(out_b + c0, pk);
           }
           if (out_f) {
 #pragma unroll
@@ -808,6 +856,17 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
         }
       }
+#ifdef GEMM_TIMING
+      if (g.dbg && ew == 0 && lane == 0) {
+        const long long te5 = clock64();
+        DBG_ADD(3, 1);
+        DBG_ADD(8, te1 - te0);
+        DBG_ADD(4, te2 - te1);
+        DBG_ADD(5, te3 - te2);
+        DBG_ADD(6, te4 - te3);
+        DBG_ADD(7, te5 - te4);
+      }
+#endif
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -815,6 +874,12 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     }
   }
 
+#ifdef GEMM_TIMING
+  if (g.dbg && threadIdx.x == 64) {
+    DBG_ADD(9, clock64() - tk0);
+    DBG_ADD(10, 1);
+  }
+#endif
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's MMAs read this CTA's smem / TMEM until here
   if (warp == 1) {
@@ -1329,7 +1394,23 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   d.ksplit = g.ksplit > 1 ? g.ksplit : 1;
   d.kb_per_slice = g.ksplit > 1 ? g.kb_per_slice : d.nkb_total;
   d.slice_rows = g.slice_rows;
+#ifdef GEMM_TIMING
+  {
+    static int want_n = -2, want_k = 0, want_res = -1;
+    if (want_n == -2) {
+      const char* e = getenv("DITREE_GEMM_DBG");   // "N,K[,resid 0/1]"
+      want_n = -1;
+      if (e) sscanf(e, "%d,%d,%d", &want_n, &want_k, &want_res);
+    }
+    d.dbg = (g.N == want_n && ktot == want_k && g.epi == EPI_GN_MISH && (want_res < 0 || (g.resid != nullptr) == (want_res != 0)) &&
+             d.num_m_tiles > 64) ? 1 : 0;
+  }
+#endif
   if (!d.out_bf16 && !d.out_f32) return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: no output");
+  // the epilogue moves 32-byte pieces of bf16 rows with 256-bit accesses
+  if ((d.out_bf16 && ((reinterpret_cast<uintptr_t>(d.out_bf16) & 31) || d.ldc % 16 != 0)) ||
+      (d.resid && ((reinterpret_cast<uintptr_t>(d.resid) & 31) || d.ld_res % 16 != 0)))
+    return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_conv_gemm: bf16 output / residual rows must be 32-byte aligned (pitch % 16 == 0)");
 
   CUtensorMap mA0, mA1, mW;
   int rc = make_act_map(ctx, &mA0, g.a[0], g.B, rows_t, nb);

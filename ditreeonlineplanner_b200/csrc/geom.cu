@@ -183,12 +183,29 @@ __device__ __forceinline__ int local_map_cell_exact(const MapView& m, double cs,
 // decides that point.  eps bounds the fp32 error per pose: five roundings of magnitude <= |x| + |y| + L +
 // (cols + rows) s / 2, each <= 2^-24 of it, plus the fp32 rounding of sin / cos / axis values (<= 2^-24
 // relative each, times |axis| <= L / 2), divided by the cell size -- with a factor 2 of slack.
-template <typename OutT>
+// kMulti: the poses come in groups of `group_size` consecutive candidates (one scenario of the device-resident
+// planner each, a multiple of the 8 poses a block handles) and group g uses the staged map slot slot_of_group[g]
+// (dt_set_map_slot): the block resolves its map through the device table before staging it.  One block per 8
+// poses, no grid stride, so a block never crosses a group.
+struct MultiMap {
+  const MapEntry* table;
+  const int32_t* slot_of_group;
+  int group_size;
+};
+
+template <typename OutT, bool kMulti>
 __global__ void __launch_bounds__(GEOM_THREADS)
 k_local_map(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
-            int64_t stride, int64_t B, int N, Axis ax, int pair, OutT* __restrict__ out) {
+            int64_t stride, int64_t B, int N, Axis ax, int pair, OutT* __restrict__ out, MultiMap mm) {
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
+  if (kMulti) {
+    const int grp = (int)((blockIdx.x * (int64_t)(blockDim.x >> 5)) / mm.group_size);
+    int slot = mm.slot_of_group[grp];
+    slot = (slot < 0 || slot >= DT_MAX_MAP_SLOTS) ? 0 : slot;
+    m = mm.table[slot].m;
+    if (m.g == nullptr) return;  // an empty slot: nothing to crop from (idle group)
+  }
   dt_stage_map(s_map, &bar, m);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -553,30 +570,33 @@ extern "C" int dt_collide_ant(dt_ctx* ctx, const float* states, int64_t row_stri
   return DT_OK;
 }
 
+// numpy.linspace(start, stop, N): arange(N) * step + start, last element forced to stop
+static Axis make_axis(int N, double scale) {
+  Axis ax;
+  volatile double L = (double)N * scale;
+  volatile double start = -L / 2 + scale / 2, stop = L / 2 - scale / 2;
+  volatile double step = (stop - start) / (double)(N - 1);
+  for (int i = 0; i < N; ++i) {
+    volatile double prod = (double)i * step;
+    ax.v[i] = prod + start;
+  }
+  ax.v[N - 1] = stop;
+  for (int i = N; i < 32; ++i) ax.v[i] = 0.0;
+  ax.amax = 0.f;
+  for (int i = 0; i < 32; ++i)
+    if (fabs(ax.v[i]) > ax.amax) ax.amax = (float)fabs(ax.v[i]) * 1.000001f;
+  ax.startf = (float)start;
+  ax.stepf = (float)step;
+  return ax;
+}
+
 extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
                             int N, double scale, int out_dtype, void* out, void* stream) {
   NEED_MAP();
   if (B <= 0) return DT_OK;
   if (!x || !y || !theta || !out) return dt_fail(ctx, DT_E_ARG, "dt_local_map: null pointer");
   if (N < 2 || N > 32) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_local_map: N must be in [2, 32]");
-  // numpy.linspace(start, stop, N): arange(N) * step + start, last element forced to stop
-  Axis ax;
-  {
-    volatile double L = (double)N * scale;
-    volatile double start = -L / 2 + scale / 2, stop = L / 2 - scale / 2;
-    volatile double step = (stop - start) / (double)(N - 1);
-    for (int i = 0; i < N; ++i) {
-      volatile double prod = (double)i * step;
-      ax.v[i] = prod + start;
-    }
-    ax.v[N - 1] = stop;
-    for (int i = N; i < 32; ++i) ax.v[i] = 0.0;
-    ax.amax = 0.f;
-    for (int i = 0; i < 32; ++i)
-      if (fabs(ax.v[i]) > ax.amax) ax.amax = (float)fabs(ax.v[i]) * 1.000001f;
-    ax.startf = (float)start;
-    ax.stepf = (float)step;
-  }
+  const Axis ax = make_axis(N, scale);
   MapView m = dt_map_view(ctx);
   const int warps = GEOM_THREADS / 32;
   int64_t blocks = (B + warps - 1) / warps;
@@ -586,15 +606,40 @@ extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const f
   const int even = ((N * N) & 1) == 0;
   if (out_dtype == DT_F32) {
     const int pair = even && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
-    k_local_map<float><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair, (float*)out);
+    k_local_map<float, false><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair,
+                                                                            (float*)out, MultiMap{nullptr, nullptr, 0});
   } else if (out_dtype == DT_BF16) {
     const int pair = even && (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-    k_local_map<__nv_bfloat16><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair,
-                                                                          (__nv_bfloat16*)out);
+    k_local_map<__nv_bfloat16, false><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(
+        m, x, y, theta, stride, B, N, ax, pair, (__nv_bfloat16*)out, MultiMap{nullptr, nullptr, 0});
   } else {
     return dt_fail(ctx, DT_E_ARG, "dt_local_map: unknown out_dtype");
   }
   DT_LAUNCH_CHECK("k_local_map");
+  return DT_OK;
+}
+
+extern "C" int dt_local_map_slots(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride,
+                                  int64_t B, int N, double scale, const int32_t* slot_of_group, int group_size,
+                                  void* out_bf16, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!ctx->d_map_table) return dt_fail(ctx, DT_E_NOMAP, "dt_set_map_slot has not been called");
+  if (B <= 0) return DT_OK;
+  if (!x || !y || !theta || !out_bf16 || !slot_of_group) return dt_fail(ctx, DT_E_ARG, "dt_local_map_slots: null pointer");
+  if (N < 2 || N > 32) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_local_map_slots: N must be in [2, 32]");
+  const int warps = GEOM_THREADS / 32;
+  if (group_size <= 0 || group_size % warps != 0 || B % group_size != 0)
+    return dt_fail(ctx, DT_E_ARG, "dt_local_map_slots: group_size must be a multiple of 8 that divides B");
+  const Axis ax = make_axis(N, scale);
+  MapView none;
+  memset(&none, 0, sizeof none);
+  const int pair = (((N * N) & 1) == 0) && (reinterpret_cast<uintptr_t>(out_bf16) & 3u) == 0;
+  const int64_t blocks = B / warps;
+  if (blocks > 0x7fffffffLL) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_local_map_slots: batch too large");
+  k_local_map<__nv_bfloat16, true><<<(int)blocks, GEOM_THREADS, ((ctx->slots_max_bytes + 15) / 16) * 16, (cudaStream_t)stream>>>(
+      none, x, y, theta, stride, B, N, ax, pair, (__nv_bfloat16*)out_bf16,
+      MultiMap{(const MapEntry*)ctx->d_map_table, slot_of_group, group_size});
+  DT_LAUNCH_CHECK("k_local_map(slots)");
   return DT_OK;
 }
 

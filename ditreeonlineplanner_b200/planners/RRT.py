@@ -74,8 +74,8 @@ class RRT_Planner(BasePlanner):
         # batched expansion flavour: "continuous" refills a slot as soon as its edge ends (every slot does
         # useful work in every device pass); "rounds" expands one batch of edges to completion at a time
         self.batch_mode = kwargs.get("batch_mode", "continuous")
-        if self.batch_mode not in ("continuous", "rounds"):
-            raise ValueError("batch_mode must be 'continuous' or 'rounds'")
+        if self.batch_mode not in ("continuous", "rounds", "device"):
+            raise ValueError("batch_mode must be 'continuous', 'rounds' or 'device'")
         self._ctx = _ctx_for(self.maze, 1.0)
         self._tree = _DeviceTree(self._ctx.device)
         self._tree.append(np.asarray(start_state[:2]))
@@ -193,8 +193,42 @@ class RRT_Planner(BasePlanner):
         pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None])
         return self._ctx.local_map(pose, n, self.local_map_scale)
 
+    def _plan_device(self):
+        """batch_mode = "device": the whole loop on the device (planners/device_planner.py, csrc/planner.cu) for this
+        one tree: 256 edge slots, no host work per pass.  run_type 0 with the uniform state sampler only."""
+        from .device_planner import DevicePlanner
+        if self.run_type != 0 or self.init_main_path is not None:
+            raise NotImplementedError("batch_mode='device' implements run_type 0; use 'continuous' for the other run types")
+        start_time = time.time()
+        cap = self.iteration_cap if self.iteration_cap is not None else 1 << 20
+        cap = max(256, (int(cap) // 256) * 256)
+        key = (cap, int(self.action_horizon), tuple(self.prop_duration_schedule))
+        dp = getattr(self.sampler, "_device_planner", None)
+        if dp is None or dp[0] != key or dp[1]._pushed >= dp[1].max_units:
+            if dp is not None:
+                dp[1].close()
+            dp = (key, DevicePlanner(self.sampler, unit_slots=1, iteration_cap=cap, action_horizon=self.action_horizon,
+                                     prop_duration=self.prop_duration_schedule, goal_sample_rate=self.goal_sample_rate,
+                                     goal_conditioning_bias=self.goal_conditioning_bias,
+                                     local_map_scale=self.local_map_scale, max_units=64))
+            self.sampler._device_planner = dp
+        unit = dict(start=np.asarray(self.start_node.state, dtype=np.float32), goal=np.asarray(self.env.goal, dtype=np.float32),
+                    maze=np.float32(self.maze), maze_name=("maze", self.maze.shape, np.float32(self.maze).tobytes()),
+                    seed=int(np.random.randint(0, 2 ** 31 - 1)))
+        rec = dp[1].run(iter([unit]), time_budget=self.time_budget)[0]
+        self.results["iterations"] = rec["results"]["iterations"]
+        self.results["number_of_nodes"] = rec["results"]["number_of_nodes"]
+        self.results["time"] = time.time() - start_time
+        if rec["path"] is None:
+            return None, None
+        self.results["path"], self.results["actions"] = rec["path"], rec["actions"]
+        self.results["path_time"] = len(rec["path"]) * self.env_dt
+        return rec["path"], rec["actions"]
+
     def plan(self):
         if self.batch_size > 1:
+            if self.batch_mode == "device":
+                return self._plan_device()
             return self._plan_continuous() if self.batch_mode == "continuous" else self._plan_batched()
         start_time = time.time()
         curr_time = time.time()

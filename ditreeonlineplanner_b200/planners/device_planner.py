@@ -1,0 +1,184 @@
+"""Device-resident, multi-scenario RRT: the host side of ``dt_plan_*`` (csrc/planner.cu).
+
+The reference plans one scenario at a time, one sampler call per loop iteration (planners/RRT.py:113-257 inside
+run_scenarios.py:202-395).  Here ``unit_slots`` (scenario, run) units grow their trees concurrently in one device
+pass -- 256 edges each, so a pass is ``unit_slots * 256`` candidates through local map -> sampler -> propagation ->
+collision -- and sampling, nearest-node search, node insertion, goal / budget tests, the final node selection and the
+path back-trace all stay on the device.  The host enqueues passes, feeds unit descriptors to the device queue and
+reads five counters with a lag of one pass; results are fetched once, at the end.
+
+Semantics are those of ``RRT_Planner(batch_size=256, batch_mode="continuous")`` (each pass advances every edge by one
+chunk and refills finished slots at once; the samples of a pass see the tree as of the start of the pass) with
+``run_type = 0``; random numbers come from per-unit Philox streams on the device, so a unit's result depends on its
+seed only -- not on the GPU count, the rank that ran it or the units that shared its passes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+EDGE_SLOTS = 256
+
+
+class DevicePlanner:
+    def __init__(self, sampler, unit_slots=8, iteration_cap=4096, action_horizon=8, prop_duration=(64,),
+                 goal_sample_rate=0.15, goal_conditioning_bias=0.85, local_map_scale=0.2, max_units=256, max_path=4096):
+        """`sampler`: the DiffusionSampler mirror that owns the packed denoiser (its max_batch should be >=
+        unit_slots * 256); the remaining arguments are RRT_Planner's (planners/RRT.py:19-31)."""
+        self.sampler = sampler
+        self.ctx = sampler._context()
+        self.lib = self.ctx.lib
+        self.U = int(unit_slots)
+        self.iteration_cap = int(iteration_cap)
+        self.max_units = int(max_units)
+        self.max_path = int(max_path)
+        cfg = L.PlanCfg()
+        cfg.unit_slots, cfg.edge_slots = self.U, EDGE_SLOTS
+        cfg.node_cap = self.iteration_cap + 1           # every node costs at least one chunk expansion
+        cfg.action_horizon = int(action_horizon)
+        sched = [max(1, int(d) // int(action_horizon)) for d in prop_duration][:8]
+        cfg.n_sched = len(sched)
+        for i, v in enumerate(sched):
+            cfg.sched_chunks[i] = v
+        cfg.iteration_cap = self.iteration_cap
+        cfg.ode_steps = int(sampler.num_diffusion_iters)
+        cfg.max_units, cfg.max_path = self.max_units, self.max_path
+        cfg.goal_sample_rate, cfg.goal_conditioning_bias = float(goal_sample_rate), float(goal_conditioning_bias)
+        cfg.local_map_scale = float(local_map_scale)
+        for i, v in enumerate(self.ctx._norm_vec(sampler.metadata)):
+            cfg.norm[i] = float(v)
+        h = C.c_void_p()
+        self.ctx._check(self.lib.dt_plan_create(self.ctx.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._maps = {}          # maze name -> (slot, rows, cols)
+        self._pushed = 0
+        self.stats = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dt_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- maps ----------------------------------------------------------------------------------------------
+    def map_slot(self, name, grid):
+        """Slot of maze `name`, staging it on first use (dt_set_map_slot)."""
+        hit = self._maps.get(name)
+        if hit is None:
+            slot = len(self._maps)
+            g = np.asarray(grid, dtype=np.float32)
+            self.ctx.set_map_slot(slot, g, 1.0)
+            hit = self._maps[name] = (slot, g.shape[0], g.shape[1])
+        return hit
+
+    # ---- the loop ------------------------------------------------------------------------------------------
+    def _push(self, units):
+        arr = (L.PlanUnit * len(units))()
+        for i, u in enumerate(units):
+            slot, rows, cols = self.map_slot(u["maze_name"], u["maze"])
+            for k in range(6):
+                arr[i].start[k] = float(u["start"][k])
+            arr[i].goal[0], arr[i].goal[1] = float(u["goal"][0]), float(u["goal"][1])
+            arr[i].half_w, arr[i].half_h = cols / 2.0, rows / 2.0   # map_width = len(maze[0]), map_length = len(maze)
+            arr[i].map_slot = slot
+            arr[i].seed = int(u["seed"]) & 0xFFFFFFFF
+            arr[i].unit_id = self._pushed + i
+        self.ctx._check(self.lib.dt_plan_push(self.h, arr, len(units), self.ctx._stream()))
+        self._pushed += len(units)
+
+    def run(self, unit_source, time_budget=None):
+        """Plan every unit `unit_source` yields (dicts with start (6,), goal (2,), maze (R,C), maze_name, seed; pulled
+        lazily, so the source may be a work queue shared between ranks).  -> list of result dicts in pull order:
+        path (n,6) | None, actions (m,2) | None, results {iterations, number_of_nodes, path_time}, runtime, goal_reached,
+        collisions, chunks."""
+        it = iter(unit_source)
+        exhausted = False
+        done = 0
+        first = self._pushed
+        t_start = time.perf_counter()
+        pass_times = {}            # plan-wide pass index -> host time at which it was seen complete
+        wait_s = 0.0
+        counters = (C.c_int32 * 5)()
+        base_pass = int(getattr(self, "_passes", 0))
+        n_pass = 0
+
+        def feed():
+            nonlocal exhausted
+            batch = []
+            while not exhausted and (self._pushed + len(batch)) - (first + done) < 2 * self.U:
+                if self._pushed + len(batch) >= self.max_units:
+                    raise RuntimeError(f"DevicePlanner: more than max_units = {self.max_units} units")
+                try:
+                    batch.append(next(it))
+                except StopIteration:
+                    exhausted = True
+            if batch:
+                self._push(batch)
+
+        feed()
+        stream = self.ctx._stream()
+        while True:
+            n_units = self._pushed - first
+            if exhausted and done >= n_units:
+                break
+            if time_budget is not None and time.perf_counter() - t_start > time_budget:
+                break
+            self.ctx._check(self.lib.dt_plan_pass(self.h, stream))
+            n_pass += 1
+            if n_pass >= 2:      # one pass stays in flight while the host looks at the one before it
+                t0 = time.perf_counter()
+                self.ctx._check(self.lib.dt_plan_counters(self.h, base_pass + n_pass - 2, 1, counters))
+                now = time.perf_counter()
+                wait_s += now - t0
+                pass_times[base_pass + n_pass - 2] = now
+                done = int(counters[2]) - self._done_before
+                if counters[4] & 1:
+                    raise RuntimeError("DevicePlanner: node capacity exhausted")
+                feed()
+        if n_pass:
+            t0 = time.perf_counter()
+            self.ctx._check(self.lib.dt_plan_counters(self.h, base_pass + n_pass - 1, 1, counters))
+            now = time.perf_counter()
+            wait_s += now - t0
+            pass_times[base_pass + n_pass - 1] = now
+            done = int(counters[2]) - self._done_before
+        self._passes = base_pass + n_pass
+        self._done_before += done
+        self.ctx.sync_status()
+        wall = time.perf_counter() - t_start
+        # results, fetched once
+        out = []
+        hdr = L.PlanResult()
+        path = np.empty((self.max_path, 6), np.float32)
+        acts = np.empty((self.max_path, 2), np.float32)
+        for uid in range(first, self._pushed):
+            self.ctx._check(self.lib.dt_plan_fetch(self.h, uid, C.byref(hdr), path.ctypes.data_as(C.c_void_p),
+                                                   acts.ctypes.data_as(C.c_void_p), self.max_path, stream))
+            finished = hdr.unit_id == uid
+            t1 = pass_times.get(hdr.last_pass, t_start + wall)
+            t0 = pass_times.get(hdr.first_pass - 1, t_start)
+            res = {"iterations": int(hdr.iterations) if finished else 0, "number_of_nodes": int(hdr.n_nodes) if finished else 0}
+            rec = dict(path=None, actions=None, results=res, runtime=max(t1 - t0, 0.0), finished=bool(finished),
+                       goal_reached=bool(hdr.goal_reached) if finished else False,
+                       collisions=int(hdr.collisions) if finished else 0, chunks=int(hdr.chunks) if finished else 0,
+                       error=int(hdr.error) if finished else 0)
+            if finished and hdr.has_path:
+                rec["path"] = path[:hdr.n_states].copy()
+                rec["actions"] = acts[:hdr.n_actions].copy()
+                res["path_time"] = hdr.n_states * 0.02      # len(path) * env.dt (base_planner.py:237)
+            out.append(rec)
+        self.stats = dict(passes=n_pass, wall_s=wall, device_wait_s=wait_s, units=len(out),
+                          candidates_per_pass=self.U * EDGE_SLOTS)
+        return out
+
+    _done_before = 0

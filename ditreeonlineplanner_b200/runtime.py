@@ -125,6 +125,27 @@ class Context:
         self.map_shape = g.shape
         self.s_global = float(s_global)
 
+    def set_map_slot(self, slot, grid, s_global=1.0):
+        """Stage `grid` in map slot `slot` (0..31) next to the main map: the per-group maps of multi-scenario passes."""
+        g = np.ascontiguousarray(np.asarray(grid, dtype=np.float32))
+        if g.ndim != 2:
+            raise ValueError("grid must be 2-D")
+        self._check(self.lib.dt_set_map_slot(self.h, int(slot), g.ctypes.data_as(C.c_void_p), g.shape[0], g.shape[1],
+                                             float(s_global), self._stream()))
+
+    def local_map_slots(self, poses, n, scale, slot_of_group, group_size):
+        """poses (B,>=3) rows in groups of `group_size`, group g cropping from map slot slot_of_group[g]
+        -> (B,n,n) bf16 holding 2m-1."""
+        st = self._f32(poses)
+        (x, y, th), stride = self._xyz(st)
+        B = st.shape[0]
+        sog = torch.as_tensor(np.asarray(slot_of_group, dtype=np.int32)).to(self.device) \
+            if not isinstance(slot_of_group, torch.Tensor) else slot_of_group.to(self.device, torch.int32)
+        out = torch.empty((B, n, n), dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.dt_local_map_slots(self.h, _ptr(x), _ptr(y), _ptr(th), stride, B, int(n), float(scale),
+                                                _ptr(sog.contiguous()), int(group_size), _ptr(out), self._stream()))
+        return out
+
     # -- geometry ---------------------------------------------------------------------------
     @staticmethod
     def _xyz(states, cols=(0, 1, 2)):

@@ -129,16 +129,68 @@ def gather_rows(local_units, local_rows, n_units_total, device, world, per_rank=
     return table
 
 
+def car_unit_descriptor(row, scenario_idx, run_idx):
+    """What the device-resident planner needs to know about one (scenario, run): start / goal exactly as
+    run_car_unit derives them (run_scenarios.py:239-246), the maze and the unit's seed."""
+    from .car_env import CarEnv
+    maze = load_maze(row["maze_name"])
+    env = CarEnv(maze_map=maze, collision_checking=False)
+    start, goal = scenario_states(row, env)
+    # reset() snaps start and goal to their cell centres and sets the heading (base_planner.py:86-90 -> car_env reset)
+    return dict(start=np.asarray(start, dtype=np.float32), goal=np.asarray(env.cell_rowcol_to_xy(
+        env.cell_xy_to_rowcol(goal[:2])), dtype=np.float32), maze=np.float32(maze), maze_name=row["maze_name"],
+        seed=unit_seed(scenario_idx, run_idx), key=(scenario_idx, run_idx))
+
+
+def run_suite_device(sampler, units_iter, rows, planner_kwargs=None):
+    """Run the units `units_iter` yields ((scenario, run) pairs, possibly from the shared queue) on the device-resident
+    multi-scenario planner.  -> (list of (scenario, run), list of result rows, planner stats)."""
+    from .planners.device_planner import DevicePlanner
+    kw = dict(unit_slots=8, iteration_cap=4096, max_units=4096)
+    kw.update(planner_kwargs or {})
+    kw.pop("batch_size", None)
+    planner = DevicePlanner(sampler, **kw)
+    mine = []
+
+    def source():
+        for s, r in units_iter:
+            mine.append((s, r))
+            yield car_unit_descriptor(rows[s], s, r)
+    try:
+        recs = planner.run(source())
+    finally:
+        stats = dict(planner.stats)
+        planner.close()
+    local = [result_row(r, rec["path"], rec["actions"], rec["results"], rec["runtime"]) for (s, r), rec in zip(mine, recs)]
+    stats["goal_reached"] = int(sum(rec["goal_reached"] for rec in recs))
+    stats["collision_rate"] = float(sum(rec["collisions"] for rec in recs)) / max(1, sum(rec["chunks"] for rec in recs))
+    return mine, local, stats
+
+
+LAST_SUITE_STATS = {}
+
+
 def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car", rank=0, world=1, device="cuda",
-              planner_kwargs=None, unit_fn=run_car_unit, schedule="queue"):
+              planner_kwargs=None, unit_fn=run_car_unit, schedule="queue", engine="host"):
     """Run this rank's share of the suite and gather everybody's rows.  -> (table, seconds).
     schedule: "queue" (default for world > 1) -- ranks pull units from a shared counter, heaviest maps first;
-    "static" -- the round-robin deal of shard_units."""
+    "static" -- the round-robin deal of shard_units.
+    engine: "host" -- one unit at a time through `unit_fn` (RRT_Planner.plan); "device" -- the device-resident
+    multi-scenario planner (planners/device_planner.py): several units share every device pass, the host only feeds
+    the device queue (from the shared counter when schedule == "queue")."""
     rows = load_scenarios(kind)
     weights = [int(np.prod(load_maze(r["maze_name"]).shape)) for r in rows]
     n_total = len(rows) * total_runs
     t0 = time.time()
-    if world > 1 and schedule == "queue":
+    queue = world > 1 and schedule == "queue"
+    if engine == "device":
+        units = queued_units(all_units(len(rows), total_runs, weights, by_weight=True), world) if queue else \
+            shard_units(len(rows), total_runs, rank, world, weights)
+        mine, local, stats = run_suite_device(sampler, units, rows, planner_kwargs)
+        LAST_SUITE_STATS.clear()
+        LAST_SUITE_STATS.update(stats)
+        table = gather_rows(mine, local, n_total, device, world, per_rank=n_total if queue else None)
+    elif queue:
         mine, local = [], []
         for s, r in queued_units(all_units(len(rows), total_runs, weights, by_weight=True), world):
             mine.append((s, r))

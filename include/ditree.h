@@ -59,6 +59,10 @@ int dt_set_option(dt_ctx* ctx, const char* name, int value);
  * cell value 1 = wall.  s_global = metres per cell (1 car, 4 ant). Synchronous on `stream`. */
 int dt_set_map(dt_ctx* ctx, const float* grid_host, int rows, int cols, float s_global, void* stream);
 
+/* Additional grids next to the main one, for passes that hold several scenarios on different mazes (the
+ * device-resident planner below; dt_local_map_slots).  slot in 0..31; same grid format as dt_set_map.  Synchronous. */
+int dt_set_map_slot(dt_ctx* ctx, int slot, const float* grid_host, int rows, int cols, float s_global, void* stream);
+
 /* ---- geometry ----------------------------------------------------------------------------- */
 /* is_colliding_car (common/map_utils.py:103-115 -> is_colliding_parallel :221-329) for B states;
  * x/y/theta strided by `stride` elements.  flags_out[b] in {0,1}.  Bit-exact vs float64 NumPy
@@ -83,6 +87,12 @@ int dt_collide_ant(dt_ctx* ctx, const float* states, int64_t row_stride, int64_t
  * the encoder's input format. */
 int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B, int N,
                  double scale, int out_dtype, void* out, void* stream);
+
+/* create_local_map for candidates that come in groups of `group_size` consecutive poses (a multiple of 8 that divides
+ * B), group g cropping from the grid staged in map slot slot_of_group[g] (device array of B / group_size int32): the
+ * per-group map index of a multi-scenario pass.  Output: (B,N,N) bf16 holding 2m-1 (the encoder's input). */
+int dt_local_map_slots(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B, int N,
+                       double scale, const int32_t* slot_of_group, int group_size, void* out_bf16, void* stream);
 
 /* check_obstacle_ahead (planners/RRT.py:61-81). */
 int dt_ray_probe(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
@@ -219,6 +229,74 @@ int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, const void*
 int dt_encode_map(dt_ctx* ctx, const void* local_map, int64_t B, float* emb_out, void* stream);
 int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* emb, const float* cond, int64_t B, float timestep,
                     float* vel_out, void* stream);
+
+/* ---- device-resident multi-scenario planner ---------------------------------------------------------------
+ * RRT_Planner.plan (planners/RRT.py:113-257) for several (scenario, run) units of the benchmark loop
+ * (run_scenarios.py:202-395) at once: unit_slots trees grow concurrently, edge_slots (= 256) edges each, one chunk
+ * of action_horizon actions per device pass.  State sampling with goal bias (base_planner.py:162-207, run_type 0),
+ * the conditioning-goal coin (RRT.py:154-157), nearest node (:49-55), local map -> sampler -> propagation ->
+ * collision (:157-184), node insertion (:195-207), the goal / iteration-cap test, the final node selection
+ * (:220-257) and the path back-trace (base_planner.py:342-363) all run on the device; units are popped from a
+ * device-side queue, so a pass needs no host decision and no device->host copy.  Random numbers: Philox4x32-10
+ * streams keyed by the unit's seed (a unit's result does not depend on which units run beside it). */
+typedef struct dt_plan dt_plan;
+
+typedef struct {
+  int32_t unit_slots;        /* U: trees grown concurrently (1..64) */
+  int32_t edge_slots;        /* S: edges in flight per tree; 256 */
+  int32_t node_cap;          /* nodes per tree (root included) */
+  int32_t action_horizon;    /* h: actions per chunk (8) */
+  int32_t n_sched;           /* entries of sched_chunks (1..8) */
+  int32_t sched_chunks[8];   /* chunks per edge by the parent's visit count: prop_duration[i] // action_horizon */
+  int32_t iteration_cap;     /* a unit ends after this many chunk expansions (sampler calls) unless it reaches the goal */
+  int32_t ode_steps;         /* K: planning_diffusion_iters */
+  int32_t max_units;         /* units this plan can hold results for; unit ids are 0..max_units-1 */
+  int32_t max_path;          /* rows reserved per unit for the final path */
+  float goal_sample_rate;    /* 0.15 (RRT.py:23) */
+  float goal_conditioning_bias; /* 0.85 */
+  double local_map_scale;    /* 0.2 */
+  double norm[16];           /* obs mean[6], obs std[6], action mean[2], action std[2] (metadata/carmaze.pt) */
+} dt_plan_cfg;
+
+typedef struct {
+  float start[6];            /* start state */
+  float goal[2];             /* goal position */
+  float half_w, half_h;      /* map_width / 2, map_length / 2: the uniform sampler's range (base_planner.py:186-187) */
+  int32_t map_slot;          /* dt_set_map_slot slot holding this unit's maze */
+  uint32_t seed;
+  int32_t unit_id;           /* 0..max_units-1, unique */
+  int32_t reserved;
+} dt_plan_unit;
+
+typedef struct {
+  int32_t unit_id;
+  int32_t goal_reached;      /* the goal disc was entered */
+  int32_t has_path;          /* a path was written (goal, or the node closest to the goal when the cap ran out) */
+  int32_t n_states, n_actions; /* rows of the path / action arrays */
+  int32_t n_nodes;           /* len(node_list) */
+  int32_t iterations;        /* chunk expansions spent */
+  int32_t first_pass, last_pass; /* plan-wide pass indices the unit started / ended in */
+  int32_t collisions;        /* chunks that ended in a collision */
+  int32_t chunks;            /* chunk expansions booked (= iterations) */
+  int32_t error;             /* 2 chain deeper than 1024, 4 path longer than max_path */
+} dt_plan_result;
+
+int dt_plan_create(dt_ctx* ctx, const dt_plan_cfg* cfg, dt_plan** out);   /* needs dt_load_denoiser first */
+void dt_plan_destroy(dt_plan* plan);
+/* Append n units (HOST array) to the device queue; idle unit slots start on them at once.  Synchronous. */
+int dt_plan_push(dt_plan* plan, const dt_plan_unit* units_host, int n, void* stream);
+/* Enqueue one pass over all unit_slots x edge_slots edges (no synchronisation) and a snapshot of the counters. */
+int dt_plan_pass(dt_plan* plan, void* stream);
+/* Counters as of the end of pass `pass_index` (0-based, one of the last four enqueued): out5 = {units popped, units
+ * pushed, units finished, passes done, error bits}.  wait = 0: returns 1 when that pass has not finished yet. */
+int dt_plan_counters(dt_plan* plan, int64_t pass_index, int wait, int32_t* out5);
+/* Result of a finished unit: header, and (when has_path) its path (n_states, 6) and actions (n_actions, 2) into HOST
+ * arrays of cap_rows rows.  Synchronous. */
+int dt_plan_fetch(dt_plan* plan, int unit_id, dt_plan_result* hdr_out, float* path_out, float* actions_out, int cap_rows,
+                  void* stream);
+/* Test hook: node count, unit id, positions (xy_out: x[cap] then y[cap]) and parents of the tree in unit slot u. */
+int dt_plan_peek_tree(dt_plan* plan, int u, int32_t* n_nodes_out, int32_t* unit_id_out, float* xy_out,
+                      int32_t* parent_out, int cap, void* stream);
 
 /* Test hook for the tcgen05 GEMM core: C[M,N] (f32) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16). */
 int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C, void* stream);

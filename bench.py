@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--denoiser", default="large")
     ap.add_argument("--maze", default="boxes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C4 / C5 legs (the `configs` object)")
     ap.add_argument("--no-suite", action="store_true", help="skip the scenario-suite (scenarios/s) leg")
     ap.add_argument("--suite-runs", type=int, default=10, help="runs per scenario in the suite leg (15 x runs units; 10 = the reference's total_runs)")
     ap.add_argument("--suite-repeats", type=int, default=3, help="timed repeats of the suite leg (median reported)")
@@ -206,6 +207,134 @@ def parity_check(args, grid, meta, sd, st_np, prev_np, noise, res, n_check=32):
             "what": "normalised K-step denoiser sample vs the fp32 oracle on the same states / noise (norm-relative); "
                     "collision / goal flags vs the float64 oracle given the device trajectory; final states of the "
                     "collision-free edges vs the float64 oracle rollout of the device's actions"}
+
+
+def secondary_configs(sampler, peaks):
+    """BASELINE.json configs[0], [3], [4] (C1 / C4 / C5), CUDA-event or wall-clock timed on this GPU, for the `configs`
+    object of the JSON line: the reference's own B = 1 loop, lidar ray-marching + one MPPI tick with 8192 rollouts, the
+    antmaze 16384-candidate pass (call sites run_scenarios_with_lidar_MPPI.py:339-341,422)."""
+    import random
+    from ditreeonlineplanner_b200 import Context, load_scenarios
+    from ditreeonlineplanner_b200 import scenarios as sc
+    from ditreeonlineplanner_b200.car_env import CarEnv
+    from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
+    from ditreeonlineplanner_b200.data import load_maze, load_metadata
+    from ditreeonlineplanner_b200.mppi import MPPI
+    from ditreeonlineplanner_b200.planners.RRT import RRT_Planner
+    from ditreeonlineplanner_b200.weights import UNET_DIMS, denoiser_flops, random_init
+
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    rng = np.random.default_rng(0)
+    ctx = sampler._context()
+    # ---- C1: RRT_Planner.plan() as the reference drives it, B = 1 ----
+    invalidate_staged_map()
+    row = load_scenarios("test_scenarios_car")[0]
+    maze = load_maze(row["maze_name"])
+    env = CarEnv(maze_map=maze, collision_checking=False)
+    start, goal_s = sc.scenario_states(row, env)
+    pl = RRT_Planner(start, goal_s, env_id="carmaze", environment=env, sampler=sampler, prediction_type="actions",
+                     action_horizon=8, local_map_size=20, local_map_scale=0.2, global_map_scale=1.0,
+                     goal_conditioning_bias=0.85, prop_duration=[64], time_budget=1e9, max_iter=300, iteration_cap=100)
+    dt_c1 = 1.0
+    for cap in (40, 1000):   # warm-up (graph capture), then timed
+        pl.iteration_cap = cap
+        torch.manual_seed(42); np.random.seed(42); random.seed(42)
+        pl.reset()
+        t0 = time.perf_counter()
+        pl.plan()
+        torch.cuda.synchronize()
+        dt_c1 = time.perf_counter() - t0
+    out["C1_reference_loop_B1"] = {"iterations_per_s": pl.results["iterations"] / dt_c1, "iterations": pl.results["iterations"],
+                                   "seconds": dt_c1, "nodes": len(pl.node_list), "scenario": row["scenario_name"],
+                                   "what": "RRT_Planner.plan(), one candidate per iteration (the reference's own loop), "
+                                           "K = 1, large denoiser, CUDA-graph replay per sampler call"}
+    # ---- C4: lidar ray-marching and one MPPI tick with 8192 rollouts ----
+    boxes = load_maze("boxes").astype(np.float32)
+    ctx.set_map(boxes)
+    invalidate_staged_map()
+    P = 4096
+    free = np.argwhere(boxes == 0)
+    cells = free[rng.integers(0, len(free), P)]
+    poses = torch.as_tensor(np.stack([cells[:, 1] + rng.uniform(0.2, 0.8, P), cells[:, 0] + rng.uniform(0.2, 0.8, P),
+                                      rng.uniform(-3, 3, P)], 1).astype(np.float32)).cuda()
+    ms = timed(lambda: ctx.lidar_scan(poses))
+    out["C4_lidar"] = {"rays_per_s": P * 181 / ms * 1e3, "poses": P, "rays": P * 181, "ms": ms}
+    ctl = MPPI(maze_data=boxes.copy(), T=16, K=8192, nx=6, nu=2)
+    state = np.array([-7.5, -7.5, 0, 1.0, 0.3, 0])
+    ctl.reset(start_state=state, goal_state=np.array([-2.5, -7.5, 0, 0, 0, 0]))
+    ctl.set_ref_path(np.stack([np.linspace(-7.5, -2.5, 100), np.full(100, -7.5)], 1))
+    noise = torch.randn((8192, 16, 2), device="cuda")
+    s_dev = torch.as_tensor(state.astype(np.float32)).cuda()
+
+    def mppi_tick():
+        cost, _ = ctl.ctx.mppi_rollout_cost(s_dev, ctl.u, noise, ctl._ref, ctl.lookahead, ctl.env.goal, ctl.collision_cost,
+                                            ctl.effort_cost)
+        u, _, _ = ctl.ctx.mppi_reduce(cost, noise, 0.02, ctl.u)
+        ctl.ctx.mppi_shift(u)
+
+    ms = timed(mppi_tick, reps=50)
+    out["C4_mppi"] = {"ms_per_tick": ms, "K": 8192, "T": 16, "rollouts_per_s": 8192 / ms * 1e3,
+                      "algorithmic_bytes_per_rollout": 16 * 2 * 4 + 4,
+                      "what": "fused rollout + collision + cost kernel, soft-min reduction (3 kernels), shift: device time of one "
+                              "control tick, inputs resident"}
+    # ---- C5: antmaze, 16384 candidates: local map + conditioning + FM sampling (large net, K = 1) + collision ----
+    huge = load_maze("random_huge").astype(np.float32)
+    actx = Context(ctx.device.index)
+    try:
+        actx.set_map(huge, 4.0)
+        meta = load_metadata("antmaze")
+        B = 16384
+        dims = UNET_DIMS["large"]
+        actx.load_denoiser(random_init(seed=0, input_dim=8, cond_dim=97, emb_dim=400, down_dims=dims), action_dim=8,
+                           horizon=16, cond_dim=97, emb_dim=400, map_size=16, down_dims=dims, max_batch=B)
+        free = np.argwhere(huge == 0)
+        cells = free[rng.integers(0, len(free), B)]
+        st = np.zeros((B, 3, 29), np.float32)
+        st[..., 0] = ((cells[:, 1] + 0.5) * 4 - 62)[:, None]
+        st[..., 1] = (62 - (cells[:, 0] + 0.5) * 4)[:, None]
+        st[..., 2:] = (meta["Observations_mean"] + meta["Observations_std"] * rng.normal(size=(B, 3, 27))).astype(np.float32)
+        obs = torch.as_tensor(st).cuda()
+        prev = torch.as_tensor((meta["Actions_mean"] + meta["Actions_std"] * rng.normal(size=(B, 8))).astype(np.float32)).cuda()
+        goal = torch.tensor([10.0, -20.0], device="cuda")
+        noise_a = torch.randn((B, 16, 8), device="cuda")
+        last = obs[:, -1, :].contiguous()
+        pose = torch.cat([last[:, :2], torch.zeros((B, 1), device="cuda")], 1)  # rollout() uses yaw = 0 for the ant
+
+        def ant_pass():
+            lm = actx.local_map(pose, 16, 0.8, bf16_signed=True)
+            cond = actx.build_cond_ant(obs, prev, goal, meta, 3, 16.0)
+            act = actx.fm_sample(noise_a, cond, lm, 1, meta["Actions_mean"], meta["Actions_std"])
+            return act, actx.collide_ant(last, 1.2)
+
+        ms = timed(ant_pass, reps=5)
+        actx.profile_begin()
+        ant_pass()
+        gemm_ms, n = actx.profile_end()
+        enc, unet = denoiser_flops(1, input_dim=8, cond_dim=97, horizon=16, map_size=16, down_dims=dims)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        out["C5_ant"] = {"candidates_per_s": B / ms * 1e3, "B": B, "ms": ms,
+                         "roofline": {"bound": "tensor", "achieved": B * (enc + unet) / (gemm_ms * 1e-3) / 1e12, "peak": peak,
+                                      "unit": "TFLOP/s", "frac": B * (enc + unet) / (gemm_ms * 1e-3) / 1e12 / peak,
+                                      "gemm_ms": gemm_ms, "gemm_launches": n},
+                         "algorithmic_gflop_per_candidate": (enc + unet) / 1e9,
+                         "tensor_bound_candidates_per_s": peak * 1e12 / (enc + unet)}
+    finally:
+        actx.close()
+    ctx.set_map(boxes)
+    invalidate_staged_map()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -473,6 +602,13 @@ def main():
                     "to whole 32-byte sectors (1216 B for 1200 B of data; the padding is NOT counted as achieved "
                     "bytes); inputs (419 MB) and trajectory (1.26 GB) exceed the 126 MB L2"}
 
+    configs = None
+    if world == 1 and not args.no_configs:
+        try:
+            configs = secondary_configs(sampler, peaks)
+        except Exception as ex:   # auxiliary: never lose the headline line to a secondary leg
+            configs = {"error": repr(ex)}
+
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = time_cpu(args, grid, meta, steps=3, warmup=1)
@@ -486,7 +622,7 @@ def main():
                            "D2H side returns what propagate_action_sequence_env returns: final states, flags, the "
                            "executed actions and the (B, S, 6) state sequences"},
             "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges, "parity_check": parity,
-            "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "suite": suite,
+            "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "suite": suite, "configs": configs,
             "clocks": clocks.summary()}
     emit(line)
     if world > 1:

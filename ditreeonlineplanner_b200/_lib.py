@@ -82,6 +82,9 @@ SIGNATURES = {
     "dt_nearest_k": (C.c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i64, C.c_int, c_p, c_p]),
     "dt_goal_cost_argmin": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_float, C.c_float, c_p, c_p, c_p]),
     "dt_mppi_reduce": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_int, C.c_float, c_p, c_p, c_p, c_p]),
+    "dt_mppi_rollout_cost": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_int, c_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, c_p, c_p, c_p]),
+    "dt_mppi_shift": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, c_p]),
     "dt_load_denoiser": (C.c_int, [c_p, C.POINTER(TensorDesc), C.c_int, C.POINTER(ModelCfg), c_p]),
     "dt_fm_sample": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_int, C.c_double, c_p, c_p, c_p]),
     "dt_encode_map": (C.c_int, [c_p, c_p, c_i64, c_p, c_p]),

@@ -331,3 +331,154 @@ extern "C" int dt_propagate_collide(dt_ctx* ctx, const float* state0, int64_t s_
   DT_LAUNCH_CHECK("k_propagate");
   return DT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// MPPI rollout cost (planners' MPPI baseline, call sites run_scenarios_with_lidar_MPPI.py:339-341,422; PARITY
+// UNPINNED: the reference's MPPI module is not in its repository).  One thread per rollout: T bicycle steps from the
+// common start state with controls u[t] + noise[k, t] (state in registers, collision test per step, the rollout
+// freezes at a collision or in the goal disc exactly like dt_propagate_collide), then
+//     cost[k] = ||p_T - target||^2 + collision_cost * collided + effort_cost * sum_t |u_t + noise_kt|^2
+// with target = ref[min(nearest(ref, p_0) + lookahead, n_ref - 1)], found by every block for itself (a few hundred
+// path points).  Replaces a broadcast copy, an add, the propagate kernel and five elementwise / reduction launches.
+// ---------------------------------------------------------------------------------------------
+struct MppiArgs {
+  const float* state;   // (6) device
+  const float* u;       // (T, 2)
+  const float* noise;   // (K, T, 2)
+  int64_t K;
+  int T;
+  const float* ref;     // (n_ref, 2)
+  int n_ref, lookahead;
+  float goal_x, goal_y, collision_cost, effort_cost;
+  float* cost;          // (K)
+  float* target_out;    // (2) or null
+};
+
+template <bool kTable>
+__global__ void __launch_bounds__(PROP_THREADS)
+k_mppi_rollout_cost(MapView m, QMapView q, MppiArgs a, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  __shared__ uint64_t bar;
+  __shared__ float s_d[PROP_THREADS / 32];
+  __shared__ int s_i[PROP_THREADS / 32];
+  __shared__ float s_target[2];
+  uint8_t* s_map = s_dyn;
+  uint32_t* s_qp = reinterpret_cast<uint32_t*>(s_dyn + m.bytes);
+  dt_stage_maps(s_map, s_qp, &bar, m, q);
+  const uint32_t s_q = dt_qmap_addr(s_qp, q);
+  const float x0 = a.state[0], y0 = a.state[1];
+  // nearest reference point to the current position: first index of the minimum squared distance (fp32)
+  float best = 3.4e38f;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < a.n_ref; j += blockDim.x) {
+    const float dx = a.ref[2 * j] - x0, dy = a.ref[2 * j + 1] - y0;
+    const float d = dx * dx + dy * dy;
+    if (d < best) {
+      best = d;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ov < best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_d[threadIdx.x >> 5] = best;
+    s_i[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_d[w] < s_d[0] || (s_d[w] == s_d[0] && s_i[w] < s_i[0])) {
+        s_d[0] = s_d[w];
+        s_i[0] = s_i[w];
+      }
+    int t = (s_i[0] == 0x7fffffff ? 0 : s_i[0]) + a.lookahead;
+    t = t > a.n_ref - 1 ? a.n_ref - 1 : t;
+    s_target[0] = a.ref[2 * t];
+    s_target[1] = a.ref[2 * t + 1];
+    if (blockIdx.x == 0 && a.target_out) {
+      a.target_out[0] = s_target[0];
+      a.target_out[1] = s_target[1];
+    }
+  }
+  __syncthreads();
+  const float tx = s_target[0], ty = s_target[1];
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < a.K; k += (int64_t)gridDim.x * blockDim.x) {
+    Car c;
+    c.x = x0; c.y = y0; c.psi = a.state[2]; c.v = a.state[3]; c.D = a.state[4]; c.dl = a.state[5];
+    dt_sincos_fast(c.psi, c.sn, c.cs);
+    EdgeState e = {-1, -1, 1};
+    const float2* nz = reinterpret_cast<const float2*>(a.noise + k * (int64_t)a.T * 2);
+    float effort = 0.f;
+    for (int i = 0; i < a.T; ++i) {
+      const float2 n2 = __ldg(nz + i);
+      const float u0 = a.u[2 * i] + n2.x, u1 = a.u[2 * i + 1] + n2.y;
+      effort += u0 * u0 + u1 * u1;
+      if (e.alive) edge_step<kTable, true>(c, e, i, u0, u1, s_map, s_q, m, q, a.goal_x, a.goal_y, status);
+    }
+    const float dx = c.x - tx, dy = c.y - ty;
+    float cost = dx * dx + dy * dy;
+    cost += a.collision_cost * (e.first >= 0 ? 1.0f : 0.0f);
+    cost += a.effort_cost * effort;
+    a.cost[k] = cost;
+  }
+}
+
+extern "C" int dt_mppi_rollout_cost(dt_ctx* ctx, const float* state, const float* u, const float* noise, int64_t K, int T,
+                                    const float* ref_xy, int n_ref, int lookahead, float goal_x, float goal_y,
+                                    float collision_cost, float effort_cost, float* cost_out, float* target_out,
+                                    void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!ctx->d_map) return dt_fail(ctx, DT_E_NOMAP, "dt_set_map has not been called");
+  if (K <= 0) return DT_OK;
+  if (!state || !u || !noise || !ref_xy || !cost_out || T < 1 || n_ref < 1 || lookahead < 0 ||
+      (reinterpret_cast<uintptr_t>(noise) & 7))
+    return dt_fail(ctx, DT_E_ARG, "dt_mppi_rollout_cost: bad argument");
+  MppiArgs a;
+  a.state = state; a.u = u; a.noise = noise; a.K = K; a.T = T; a.ref = ref_xy; a.n_ref = n_ref; a.lookahead = lookahead;
+  a.goal_x = goal_x; a.goal_y = goal_y; a.collision_cost = collision_cost; a.effort_cost = effort_cost;
+  a.cost = cost_out; a.target_out = target_out;
+  const MapView m = dt_map_view(ctx);
+  const QMapView q = dt_qmap_view(ctx);
+  const size_t smem = (size_t)m.bytes + (size_t)q.bytes;
+  static unsigned long long attr_set = 0;
+  const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+  if (!(attr_set & dev_bit)) {
+    DT_CUDA(cudaFuncSetAttribute(k_mppi_rollout_cost<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_mppi_rollout_cost<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set |= dev_bit;
+  }
+  int64_t blocks = (K + PROP_THREADS - 1) / PROP_THREADS;
+  if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+  if (q.g) k_mppi_rollout_cost<true><<<(int)blocks, PROP_THREADS, smem, (cudaStream_t)stream>>>(m, q, a, ctx->d_status);
+  else k_mppi_rollout_cost<false><<<(int)blocks, PROP_THREADS, smem, (cudaStream_t)stream>>>(m, q, a, ctx->d_status);
+  DT_LAUNCH_CHECK("k_mppi_rollout_cost");
+  return DT_OK;
+}
+
+// first action out, control sequence shifted left by one step (the last step repeats): the end of an MPPI tick
+__global__ void k_mppi_shift(float* __restrict__ u, int T, int A, float* __restrict__ action_out) {
+  __shared__ float s_u[1024];
+  const int n = T * A;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_u[i] = u[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (i < A && action_out) action_out[i] = s_u[i];
+    const int src = i + A < n ? i + A : i;
+    u[i] = s_u[src];
+  }
+}
+
+extern "C" int dt_mppi_shift(dt_ctx* ctx, float* u_inout, int T, int A, float* action_out, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!u_inout || T < 1 || A < 1 || T * A > 1024) return dt_fail(ctx, DT_E_ARG, "dt_mppi_shift: bad argument");
+  k_mppi_shift<<<1, 256, 0, (cudaStream_t)stream>>>(u_inout, T, A, action_out);
+  DT_LAUNCH_CHECK("k_mppi_shift");
+  return DT_OK;
+}

@@ -57,31 +57,40 @@ class MPPI:
         return self.env.is_done(state)
 
     def rollout_costs(self, state, noise):
-        """K rollouts of T steps from `state` with controls u + noise -> (cost (K,), result dict)."""
+        """K rollouts of T steps from `state` with controls u + noise -> (cost (K,), target (2,)): ONE kernel
+        (dt_mppi_rollout_cost: rollout, collision, look-ahead target, tracking / collision / effort cost)."""
+        ctx = self.ctx = _ctx_for(self.maze, 1.0)
+        s0 = torch.as_tensor(np.asarray(state, dtype=np.float32)).to(ctx.device, non_blocking=True)
+        return ctx.mppi_rollout_cost(s0, self.u, noise, self._ref, self.lookahead, self.env.goal, self.collision_cost,
+                                     self.effort_cost)
+
+    def rollout_costs_reference(self, state, noise):
+        """The same cost formed with the propagate kernel and elementwise torch ops (what rollout_costs fused): kept as
+        the comparison for the kernel's test."""
         ctx = self.ctx = _ctx_for(self.maze, 1.0)
         s0 = torch.as_tensor(np.asarray(state, dtype=np.float32), device=ctx.device).expand(self.K, 6).contiguous()
         actions = (self.u[None] + noise).contiguous()
         res = ctx.propagate_collide(s0, actions, self.env.goal, want_traj=False, stop_on_collision=True)
         final = res["final"]
-        # track the reference path: squared distance of the rollout's end to the look-ahead point
         cur = torch.as_tensor(np.asarray(state[:2], dtype=np.float32), device=ctx.device)
         near = int(torch.argmin(((self._ref - cur) ** 2).sum(1)))
         target = self._ref[min(near + self.lookahead, len(self._ref) - 1)]
         cost = ((final[:, :2] - target) ** 2).sum(1)
         cost = cost + self.collision_cost * (res["first_coll"] >= 0).float()
         cost = cost + self.effort_cost * (actions ** 2).sum((1, 2))
-        return cost, res
+        return cost, target
 
     def step(self, curr_state):
-        """-> (next_state, applied action, done) with done None on collision (driver convention :422-424)."""
+        """-> (next_state, applied action, done) with done None on collision (driver convention :422-424).
+        Device side of a tick: noise, rollout + cost, soft-min reduction, shift -- no host synchronisation until the
+        applied action is read back."""
         if self._ref is None:
             raise ValueError("set_ref_path() must be called before step()")
         dev = self.ctx.device
         noise = torch.randn((self.K, self.T, self.nu), device=dev) * self.sigma
         cost, _ = self.rollout_costs(curr_state, noise)
         self.u, _, _ = self.ctx.mppi_reduce(cost, noise, self.lam, self.u)
-        action = self.u[0].cpu().numpy().astype(np.float64)
-        self.u = torch.cat([self.u[1:], self.u[-1:]], 0)
+        action = self.ctx.mppi_shift(self.u).cpu().numpy().astype(np.float64)
         self.env.set_state(np.asarray(curr_state, dtype=np.float64))
         self.env.collision_checking = True
         obs, _, terminated, _, info = self.env.step(action)

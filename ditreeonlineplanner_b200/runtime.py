@@ -338,6 +338,28 @@ class Context:
                                             self._stream()))
         return u, amin, w
 
+    def mppi_rollout_cost(self, state, u, noise, ref_xy, lookahead, goal_xy, collision_cost, effort_cost):
+        """-> (cost (K,), target (2,)) for K rollouts of T steps from one state (fused rollout + cost kernel)."""
+        st = self._f32(state).contiguous()
+        uu = self._f32(u).contiguous()
+        nz = self._f32(noise).contiguous()
+        ref = self._f32(ref_xy).contiguous()
+        K, T = nz.shape[0], nz.shape[1]
+        cost = torch.empty(K, dtype=torch.float32, device=self.device)
+        target = torch.empty(2, dtype=torch.float32, device=self.device)
+        self._check(self.lib.dt_mppi_rollout_cost(self.h, _ptr(st), _ptr(uu), _ptr(nz), K, T, _ptr(ref), ref.shape[0],
+                                                  int(lookahead), float(goal_xy[0]), float(goal_xy[1]),
+                                                  float(collision_cost), float(effort_cost), _ptr(cost), _ptr(target),
+                                                  self._stream()))
+        return cost, target
+
+    def mppi_shift(self, u):
+        """In place: u <- u shifted left by one step (last step repeated); returns the action that was u[0]."""
+        assert u.is_contiguous() and u.dtype == torch.float32 and u.device == self.device
+        act = torch.empty(u.shape[1], dtype=torch.float32, device=self.device)
+        self._check(self.lib.dt_mppi_shift(self.h, _ptr(u), u.shape[0], u.shape[1], _ptr(act), self._stream()))
+        return act
+
     # -- probability-map state sampler (run_type >= 2) -----------------------------------------
     def _f64(self, t):
         if not isinstance(t, torch.Tensor):

@@ -171,6 +171,19 @@ int dt_goal_cost_argmin(dt_ctx* ctx, const float* node_x, const float* node_y, i
 int dt_mppi_reduce(dt_ctx* ctx, const float* cost, const float* noise, int64_t K, int TA, float lambda, float* u_inout,
                    int32_t* argmin_out, float* weights_out, void* stream);
 
+/* MPPI rollout cost for K rollouts of T steps from ONE start state (device, 6 floats) with controls u (T,2) + noise
+ * (K,T,2): bicycle rollout with per-step collision / goal test fused with the cost
+ *   cost[k] = ||p_T - target||^2 + collision_cost * collided + effort_cost * sum_t |u_t + noise_kt|^2,
+ * target = ref_xy[min(argmin_j ||ref_j - p_0|| + lookahead, n_ref - 1)] (also written to target_out when not NULL).
+ * PARITY UNPINNED like dt_mppi_reduce (the reference's MPPI module is absent); the call sites are
+ * run_scenarios_with_lidar_MPPI.py:339-341,422. */
+int dt_mppi_rollout_cost(dt_ctx* ctx, const float* state, const float* u, const float* noise, int64_t K, int T,
+                         const float* ref_xy, int n_ref, int lookahead, float goal_x, float goal_y, float collision_cost,
+                         float effort_cost, float* cost_out, float* target_out, void* stream);
+
+/* End of an MPPI tick: action_out (A, nullable) = u[0]; u shifted left by one step, the last step repeated. */
+int dt_mppi_shift(dt_ctx* ctx, float* u_inout, int T, int A, float* action_out, void* stream);
+
 /* ---- probability-map state sampler (run_type >= 2) -------------------------------------------- */
 /* CarEnv.prior (car_env.py:100-101, maze_map setter :117-121): exact Euclidean distance transform of the
  * free cells of the ctx map (scipy.ndimage.distance_transform_edt(1 - maze)) divided by its sum.

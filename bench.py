@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C4 / C5 legs (the `configs` object)")
     ap.add_argument("--no-suite", action="store_true", help="skip the scenario-suite (scenarios/s) leg")
-    ap.add_argument("--suite-runs", type=int, default=10, help="runs per scenario in the suite leg (15 x runs units; 10 = the reference's total_runs)")
+    ap.add_argument("--suite-runs", type=int, default=40, help="runs per scenario in the suite leg (15 x runs units; the reference's __main__ uses 10: 40 keeps the leg seconds long on 8 GPUs)")
     ap.add_argument("--suite-repeats", type=int, default=3, help="timed repeats of the suite leg (median reported)")
     ap.add_argument("--suite-unit-slots", type=int, default=8, help="trees grown concurrently per device pass (x 256 edges)")
     ap.add_argument("--prop-batch", type=int, default=1 << 20, help="candidates for the propagate+collide roofline leg")

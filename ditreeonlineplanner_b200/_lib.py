@@ -90,6 +90,8 @@ SIGNATURES = {
     "dt_encode_map": (C.c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "dt_unet_forward": (C.c_int, [c_p, c_p, c_p, c_p, c_i64, C.c_float, c_p, c_p]),
     "dt_gemm_bf16": (C.c_int, [c_p, c_p, c_p, c_i64, C.c_int, C.c_int, c_p, c_p]),
+    "dt_conv2d_gn_bf16": (C.c_int, [c_p, c_p, c_i64, C.c_int, C.c_int, C.c_int, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p,
+                                    c_p, C.c_int, c_p, c_p]),
     "dt_profile_begin": (C.c_int, [c_p]),
     "dt_profile_end": (C.c_int, [c_p, C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "dt_profile_csv": (C.c_int, [c_p, C.c_char_p]),

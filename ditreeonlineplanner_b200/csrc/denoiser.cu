@@ -951,21 +951,58 @@ static int unet_body(dt_ctx* ctx, dt_denoiser* d, int64_t B, const float* film_t
 }
 
 // ---- encoder ---------------------------------------------------------------------------------
-static int enc_conv(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bfloat16* in, int64_t B, int H, int W,
-                    int Cin, int k, int stride, int pad, int OH, int OW, __nv_bfloat16* out, cudaStream_t st) {
+// One ResNet conv + its GroupNorm(C / 16) (+ residual) (+ ReLU) as ONE tcgen05 GEMM launch (gemm.cu, EPI_GN_RELU):
+//   * Cin a multiple of 64 (every conv but the stem): the input (B, H, W, Cin) is the GEMM's A operand through a 4-D
+//     TMA tensor map (channel, x, y, sample) -- a conv tap is an (x, y) offset of the box, the conv stride is the
+//     TMA traversal stride, the zero padding is TMA's out-of-bounds fill; nothing is im2col'ed;
+//   * one output pixel per sample (the last stage on small local maps): the taps that only meet padding are left
+//     out (K = valid taps x Cin) and the input is read as H W "time steps";
+//   * the stem (Cin = 1, 7 x 7): im2col (49 -> 64 columns), then the same fused epilogue.
+// Maps with more than 128 output pixels per sample do not fit the one-tile-holds-whole-samples epilogue and take the
+// unfused path (im2col -> GEMM -> k_gn2d).
+static int gn2d(dt_ctx* ctx, const ConvW& w, __nv_bfloat16* x, int64_t B, int HW, int C, const __nv_bfloat16* resid,
+                int relu, __nv_bfloat16* out, cudaStream_t st) {
+  const int64_t warps = B * (C / 16);
+  int64_t blocks = (warps + 7) / 8;
+  if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+  k_gn2d<<<(int)blocks, 256, 0, st>>>(x, B, HW, C, w.gamma, w.beta, resid, relu, out);
+  DT_LAUNCH_CHECK("k_gn2d");
+  return DT_OK;
+}
+
+static int enc_conv_gn(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bfloat16* in, int64_t B, int H, int W,
+                       int Cin, int k, int stride, int pad, int OH, int OW, const __nv_bfloat16* resid, int relu,
+                       __nv_bfloat16* out, cudaStream_t st) {
   const int64_t rows = B * OH * OW;
-  if (OH == 1 && OW == 1 && H * W <= GEMM_MAX_SEG && Cin % 64 == 0 && w.Ktot == k * k * Cin) {
-    // One output pixel per sample (the last ResNet stage on small local maps): the taps that land on the
-    // zero padding contribute nothing, and the ones that land on the map meet its pixels in row-major order,
-    // so the input itself is the GEMM's A operand -- (B, H W, Cin) read as H W "time steps" -- and each valid
-    // tap is one K segment over its own slice of the packed weights.  No im2col, K = (valid taps) x Cin
-    // instead of k k Cin (512 instead of 4608 on a 1 x 1 map); the dropped products were exact zeros.
-    ConvGemm g;
+  const int T = OH * OW;
+  ConvGemm g;
+  g.n_src = 1;
+  g.w = w.w;
+  g.N = w.N;
+  g.B = B;
+  g.T = T;
+  g.bias = w.bias;
+  g.out_bf16 = out;
+  g.ldc = w.N;
+  g.out_b_stride = T;
+  g.out_t_stride = 1;
+  const bool fused = T <= 128 && w.N % 64 == 0;
+  if (fused) {
+    g.epi = EPI_GN_RELU;
+    g.gamma = w.gamma;
+    g.beta = w.beta;
+    g.group_width = 16;
+    g.resid = resid;
+    g.ld_res = w.N;
+    g.relu = relu;
+  } else {
+    g.epi = EPI_PLAIN;
+  }
+  bool direct = false;
+  if (fused && OH == 1 && OW == 1 && H * W <= GEMM_MAX_SEG && Cin % 64 == 0 && w.Ktot == k * k * Cin) {
+    // one output pixel per sample: valid taps only, the input read as H W time steps
     g.a[0] = ActSrc{in, Cin, H * W, 1};
-    g.n_src = 1;
-    g.w = w.w;
     g.w_ktot = w.Ktot;
-    g.N = w.N;
     g.nseg = 0;
     int next_tap = 0;  // first weight tap not yet consumed or skipped
     for (int ky = 0; ky < k; ++ky) {
@@ -977,55 +1014,46 @@ static int enc_conv(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bflo
         next_tap = tap + 1;
       }
     }
-    g.B = B;
-    g.T = 1;
-    g.epi = EPI_PLAIN;
-    g.bias = w.bias;
-    g.out_bf16 = out;
-    g.ldc = w.N;
-    g.out_b_stride = 1;
-    return dt_conv_gemm(ctx, g, st);
+    direct = true;
+  } else if (fused && Cin % 64 == 0 && w.Ktot == k * k * Cin && k * k <= GEMM_MAX_SEG) {
+    ActSrc a{in, Cin, 0, 1};
+    a.W2 = W; a.H2 = H; a.stride2 = stride; a.ow2 = OW; a.oh2 = OH;
+    g.a[0] = a;
+    g.nseg = 0;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) g.seg[g.nseg++] = GemmSeg{0, kx - pad, ky - pad, Cin / 64, 0};
+    direct = true;
   }
-  if (Cin % 8 == 0 && w.Ktot == k * k * Cin) {
-    k_im2col_v8<<<ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
-    DT_LAUNCH_CHECK("k_im2col_v8");
-  } else {
-    k_im2col<<<ew_grid(rows * w.Ktot, ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
-    DT_LAUNCH_CHECK("k_im2col");
+  if (!direct) {
+    if (Cin % 8 == 0 && w.Ktot == k * k * Cin) {
+      k_im2col_v8<<<ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
+      DT_LAUNCH_CHECK("k_im2col_v8");
+    } else {
+      k_im2col<<<ew_grid(rows * w.Ktot, ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
+      DT_LAUNCH_CHECK("k_im2col");
+    }
+    g.nseg = 1;
+    g.seg[0] = GemmSeg{0, 0, 0, w.Ktot / 64, 0};
+    if (fused) {
+      g.a[0] = ActSrc{d->col, w.Ktot, T, 1};      // the im2col matrix as B samples of T rows
+    } else {
+      g.a[0] = ActSrc{d->col, w.Ktot, (int)rows, 1};
+      g.B = 1;
+      g.T = (int)rows;
+      g.out_b_stride = 0;
+    }
   }
-  ConvGemm g;
-  g.a[0] = ActSrc{d->col, w.Ktot, (int)rows, 1};
-  g.n_src = 1;
-  g.w = w.w;
-  g.N = w.N;
-  g.nseg = 1;
-  g.seg[0] = GemmSeg{0, 0, 0, w.Ktot / 64};
-  g.B = 1;
-  g.T = (int)rows;
-  g.epi = EPI_PLAIN;
-  g.bias = w.bias;
-  g.out_bf16 = out;
-  g.ldc = w.N;
-  return dt_conv_gemm(ctx, g, st);
-}
-
-static int gn2d(dt_ctx* ctx, const ConvW& w, __nv_bfloat16* x, int64_t B, int HW, int C, const __nv_bfloat16* resid,
-                int relu, __nv_bfloat16* out, cudaStream_t st) {
-  const int64_t warps = B * (C / 16);
-  int64_t blocks = (warps + 7) / 8;
-  if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
-  k_gn2d<<<(int)blocks, 256, 0, st>>>(x, B, HW, C, w.gamma, w.beta, resid, relu, out);
-  DT_LAUNCH_CHECK("k_gn2d");
-  return DT_OK;
+  int rc = dt_conv_gemm(ctx, g, st);
+  if (rc || fused) return rc;
+  return gn2d(ctx, w, out, B, T, w.N, resid, relu, out, st);
 }
 
 // local map (B,N,N) bf16 in [-1,1] -> d->emb (B, emb_pad) f32
 static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm, int64_t B, cudaStream_t st) {
   const int NM = d->NM;
   int rc;
-  int H = (NM + 6 - 7) / 2 + 1;  // conv1 7x7 s2 p3
-  if ((rc = enc_conv(ctx, d, d->enc_conv1, lm, B, NM, NM, 1, 7, 2, 3, H, H, d->e[0], st))) return rc;
-  if ((rc = gn2d(ctx, d->enc_conv1, d->e[0], B, H * H, 64, nullptr, 1, d->e[1], st))) return rc;
+  int H = (NM + 6 - 7) / 2 + 1;  // conv1 7x7 s2 p3, then GroupNorm + ReLU
+  if ((rc = enc_conv_gn(ctx, d, d->enc_conv1, lm, B, NM, NM, 1, 7, 2, 3, H, H, nullptr, 1, d->e[1], st))) return rc;
   const int PH = (H + 2 - 3) / 2 + 1;  // maxpool 3x3 s2 p1
   k_maxpool3s2<<<ew_grid(B * PH * PH * 64, ctx), 256, 0, st>>>(d->e[1], B, H, H, 64, PH, PH, d->e[0]);
   DT_LAUNCH_CHECK("k_maxpool3s2");
@@ -1039,18 +1067,15 @@ static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm,
       const EncBlockW& eb = d->enc[li][b];
       const int OH = (H + 2 - 3) / eb.stride + 1;
       // y = relu(gn(conv1(x)))
-      if ((rc = enc_conv(ctx, d, eb.c1, cur, B, H, H, eb.cin, 3, eb.stride, 1, OH, OH, t1, st))) return rc;
-      if ((rc = gn2d(ctx, eb.c1, t1, B, OH * OH, eb.cout, nullptr, 1, t1, st))) return rc;
-      // identity / downsample branch
+      if ((rc = enc_conv_gn(ctx, d, eb.c1, cur, B, H, H, eb.cin, 3, eb.stride, 1, OH, OH, nullptr, 1, t1, st))) return rc;
+      // identity / downsample branch: gn(conv1x1(x))
       const __nv_bfloat16* idt = cur;
       if (eb.has_ds) {
-        if ((rc = enc_conv(ctx, d, eb.ds, cur, B, H, H, eb.cin, 1, eb.stride, 0, OH, OH, t3, st))) return rc;
-        if ((rc = gn2d(ctx, eb.ds, t3, B, OH * OH, eb.cout, nullptr, 0, t3, st))) return rc;
+        if ((rc = enc_conv_gn(ctx, d, eb.ds, cur, B, H, H, eb.cin, 1, eb.stride, 0, OH, OH, nullptr, 0, t3, st))) return rc;
         idt = t3;
       }
       // out = relu(gn(conv2(y)) + identity)
-      if ((rc = enc_conv(ctx, d, eb.c2, t1, B, OH, OH, eb.cout, 3, 1, 1, OH, OH, t2, st))) return rc;
-      if ((rc = gn2d(ctx, eb.c2, t2, B, OH * OH, eb.cout, idt, 1, t2, st))) return rc;
+      if ((rc = enc_conv_gn(ctx, d, eb.c2, t1, B, OH, OH, eb.cout, 3, 1, 1, OH, OH, idt, 1, t2, st))) return rc;
       __nv_bfloat16* nxt = t2;
       t2 = cur;
       cur = nxt;

@@ -321,6 +321,7 @@ struct GemmDev {
   int ksplit, kb_per_slice;
   long long slice_rows;
   int dbg;   // GEMM_TIMING builds: account this launch
+  int a_tile_bytes;  // bytes one activation TMA load delivers (rows_t * nb * 128; 16384 unless a tile is partly empty)
 };
 
 template <int BN, int CG>
@@ -436,11 +437,11 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             const uint32_t sa = base + stage * P::kStage;
             if (CG == 2) {
               // both CTAs' bytes complete on the LEADER's full barrier; only the leader arms it
-              if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * P::kStage);
+              if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (g.a_tile_bytes + P::kStageB));
               tma2_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
               tma2_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, (kw + wofs) * BK, n_tile * BN + (int)rank * (BN / 2));
             } else {
-              mbar_expect_tx(bar_full + 8 * stage, P::kStage);
+              mbar_expect_tx(bar_full + 8 * stage, g.a_tile_bytes + P::kStageB);
               tma_load_4d(sa, mA, bar_full + 8 * stage, blk * BK, sg.phase, t_base + sg.t_off, b_base);
               tma_load_2d(sa + P::kStageA, &mapW, bar_full + 8 * stage, (kw + wofs) * BK, n_tile * BN);
             }
@@ -562,6 +563,10 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rp) + o));
         }
       }
+      if (EPI == EPI_GN_RELU) {
+        pf_par[1] = __ldg(g.gamma + n0_ + pcol);
+        pf_par[2] = __ldg(g.beta + n0_ + pcol);
+      }
       if (EPI == EPI_GN_MISH) {
         pf_par[1] = __ldg(g.gamma + n0_ + pcol);
         pf_par[2] = __ldg(g.beta + n0_ + pcol);
@@ -597,17 +602,19 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         b = (long long)m_tile * g.nb + row / g.T;
         t = row % g.T;
       }
-      const bool valid = (b < g.B) && (t < g.T);
+      // (a tile of whole samples may be partly empty when T does not divide 128: those rows belong to nobody)
+      const bool valid = (b < g.B) && (t < g.T) && (g.tiles_per_sample > 0 || row < g.nb * g.T);
       DBG_T(te0);
       // publish this tile's (prefetched) parameters; the first barrier orders the previous tile's readers
       epi_bar_sync();
       if (et < BN) {
         s_par[et] = pf_par[0];
-        if (EPI == EPI_GN_MISH) {
+        if (EPI != EPI_PLAIN) {
           s_par[BN + et] = pf_par[1];
           s_par[2 * BN + et] = pf_par[2];
         }
       }
+
       if (film_smem) {
 #pragma unroll
         for (int j = 0; j < PF; ++j) {
@@ -630,6 +637,103 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
       const long long out_row = b * g.out_b_stride + (long long)t * g.out_t_stride + g.out_off + slice * g.slice_rows;
       const float* sp = s_par + half * HALF;  // this warp's column window of the staged parameters
+
+      if constexpr (EPI == EPI_GN_RELU) {
+        // ---- ResNet encoder: GroupNorm over (T rows x 16 channels) per sample, any T <= 128 ----
+        // Deterministic (no atomics: the same inputs give the same bits whatever shares the tile): every row leaves
+        // its partial sums in shared memory, then one thread per (sample, group) adds the T rows in row order.
+        constexpr int NGT = BN / 16;          // groups per tile; one 16-column TMEM chunk is exactly one group
+        constexpr int NCHR = HALF / 16;       // chunks (= groups) per epilogue warp
+        float* s_part = s_film;               // [row][group][sum, sum of squares]   (128 * NGT * 2 floats)
+        float* s_ms = s_red;                  // [sample][group][mean, rstd]          (T >= 2: <= 64 * NGT * 2 floats)
+        const int smp_l = row / g.T;          // sample inside the tile (rows >= nb * T are nobody's: `valid` is false)
+        const float inv_n = 1.0f / (float)(g.T * 16);
+        float own_mean[NCHR], own_rstd[NCHR]; // T == 1: a row is a whole sample
+        uint32_t rr[2][CH];
+        tmem_ld16(taddr, rr[0]);
+#pragma unroll
+        for (int c = 0; c < NCHR; ++c) {
+          tmem_wait(rr[c & 1]);
+          if (c + 1 < NCHR) tmem_ld16(taddr + (c + 1) * CH, rr[(c + 1) & 1]);
+          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float v = __uint_as_float(rr[c & 1][j]) + sp[c * CH + j];
+            sm += v;
+            sq = fmaf(v, v, sq);
+          }
+          // (no divergence around the warp-aligned tcgen05.ld / wait of the next iteration: every lane stores)
+          float* pp = s_part + (row * NGT + half * NCHR + c) * 2;
+          pp[0] = valid ? sm : 0.f;
+          pp[1] = valid ? sq : 0.f;
+          own_mean[c] = sm * inv_n;
+          own_rstd[c] = rsqrtf(fmaxf(sq * inv_n - own_mean[c] * own_mean[c], 0.f) + 1e-5f);
+        }
+        if (g.T > 1) {
+          epi_bar_sync();
+          for (int pr = et; pr < g.nb * NGT; pr += NET) {
+            const int smp = pr / NGT, grp = pr - smp * NGT;
+            const float* pp = s_part + (smp * g.T * NGT + grp) * 2;
+            float a0 = 0.f, a1 = 0.f;
+            for (int r = 0; r < g.T; ++r) {
+              a0 += pp[r * NGT * 2];
+              a1 += pp[r * NGT * 2 + 1];
+            }
+            const float mean = a0 * inv_n;
+            s_ms[pr * 2] = mean;
+            s_ms[pr * 2 + 1] = rsqrtf(fmaxf(a1 * inv_n - mean * mean, 0.f) + 1e-5f);
+          }
+          epi_bar_sync();
+        }
+        const __nv_bfloat16* res_row = (g.resid && valid) ? g.resid + out_row * g.ld_res + n0 + half * HALF : nullptr;
+        __nv_bfloat16* out_b = g.out_bf16 + out_row * g.ldc + n0 + half * HALF;
+        tmem_ld16(taddr, rr[0]);
+#pragma unroll
+        for (int c = 0; c < NCHR; ++c) {
+          tmem_wait(rr[c & 1]);
+          if (c + 1 < NCHR) {
+            tmem_ld16(taddr + (c + 1) * CH, rr[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+              else mbar_arrive_relaxed(bar_tempty + 8 * acc);
+            }
+          }
+          uint32_t rs8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (res_row) ldg256(res_row + c * CH, rs8);
+          __syncwarp();
+          const float* ms = s_ms + ((valid ? smp_l : 0) * NGT + half * NCHR + c) * 2;
+          const float mean = g.T > 1 ? ms[0] : own_mean[c];
+          const float rstd = g.T > 1 ? ms[1] : own_rstd[c];
+          uint32_t pk[CH / 2];
+#pragma unroll
+          for (int u = 0; u < CH / 2; ++u) {
+            float y0 = __uint_as_float(rr[c & 1][2 * u]) + sp[c * CH + 2 * u];
+            float y1 = __uint_as_float(rr[c & 1][2 * u + 1]) + sp[c * CH + 2 * u + 1];
+            y0 = fmaf((y0 - mean) * rstd, sp[BN + c * CH + 2 * u], sp[2 * BN + c * CH + 2 * u]);
+            y1 = fmaf((y1 - mean) * rstd, sp[BN + c * CH + 2 * u + 1], sp[2 * BN + c * CH + 2 * u + 1]);
+            if (res_row) {
+              y0 += __uint_as_float(rs8[u] << 16);
+              y1 += __uint_as_float(rs8[u] & 0xFFFF0000u);
+            }
+            if (g.relu) {
+              y0 = fmaxf(y0, 0.f);
+              y1 = fmaxf(y1, 0.f);
+            }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+            pk[u] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          if (valid) stg256(out_b + c * CH, pk);
+          __syncwarp();
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
 
       // GroupNorm groups seen by this warp's column slice: NLG whole groups when a group fits in the
       // slice, otherwise the slice is part of ONE group that spans SPG slices.
@@ -914,6 +1018,28 @@ static PFN_tmapEncodeTiled get_encode() {
 static int make_act_map(dt_ctx* ctx, CUtensorMap* m, const ActSrc& a, int64_t B, int rows_t, int nb) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return dt_fail(ctx, DT_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if (a.W2 > 0) {
+    // 2-D conv source (B, H2, W2, C): the box is one tap's view of nb samples' output maps -- ow2 x oh2 pixels read
+    // with the conv stride (TMA traversal stride), rows land in shared memory as (sample, oy, ox), 64 channels each
+    const int s = a.stride2;
+    const int bw = (a.ow2 - 1) * s + 1, bh = (a.oh2 - 1) * s + 1;
+    if (a.C % 8 != 0 || s < 1 || bw > 256 || bh > 256 || nb > 256 || a.ow2 * a.oh2 != rows_t)
+      return dt_fail(ctx, DT_E_UNSUPPORTED, "2-D activation shape not TMA-addressable");
+    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W2, (cuuint64_t)a.H2, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.W2 * a.C * 2, (cuuint64_t)a.H2 * a.W2 * a.C * 2};
+    cuuint32_t box[4] = {BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act2d C=%d W=%d H=%d s=%d ow=%d oh=%d nb=%d) failed: %d", a.C, a.W2,
+               a.H2, s, a.ow2, a.oh2, nb, (int)r);
+      return dt_fail(ctx, DT_E_CUDA, buf);
+    }
+    return DT_OK;
+  }
   if (a.C % 8 != 0 || a.T_in % a.P != 0) return dt_fail(ctx, DT_E_UNSUPPORTED, "activation shape not TMA-addressable");
   cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.P, (cuuint64_t)(a.T_in / a.P), (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.P * a.C * 2, (cuuint64_t)a.T_in * a.C * 2};
@@ -1188,7 +1314,7 @@ k_splitk_epi(SplitKEpi p) {
     }
   }
   float mean = 0.f, rstd = 1.f;
-  if (p.epi == EPI_GN_MISH) {
+  if (p.epi != EPI_PLAIN) {
     s_a[threadIdx.x] = s;
     s_b[threadIdx.x] = ss;
     __syncthreads();
@@ -1218,6 +1344,7 @@ k_splitk_epi(SplitKEpi p) {
   for (int i = threadIdx.x; i < cnt; i += SPLITK_EPI_THREADS) {  // a thread revisits the elements it wrote itself
     const int t = t_first + i / p.gw, c = i % p.gw, n = n0 + c;
     float v = s_y[i];
+    if (p.epi == EPI_GN_RELU) v = (v - mean) * rstd * p.gamma[n] + p.beta[n];   // residual, then ReLU, below
     if (p.epi == EPI_GN_MISH) {
       v = mish_f((v - mean) * rstd * p.gamma[n] + p.beta[n]);
       if (p.film) {
@@ -1228,7 +1355,7 @@ k_splitk_epi(SplitKEpi p) {
     }
     const long long row = (long long)b * p.out_b_stride + (long long)t * p.out_t_stride + p.out_off;
     if (p.resid) v += __bfloat162float(p.resid[row * p.ld_res + n]);
-    if (p.epi == EPI_PLAIN && p.relu) v = fmaxf(v, 0.f);
+    if (p.epi != EPI_GN_MISH && p.relu) v = fmaxf(v, 0.f);
     if (p.out_bf16) p.out_bf16[row * p.ldc + n] = __float2bfloat16(v);
     if (p.out_f32) p.out_f32[row * p.ldc + n] = v;
   }
@@ -1244,7 +1371,9 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   // two shapes qualify: (a) whole samples inside ONE 128-row tile (the U-Net at a few candidates), and
   // (b) a flat [rows, N] problem -- one "sample", plain epilogue -- with a handful of 128-row tiles and a
   // long K (the encoder's last stages at planner batch sizes: 256 x 512 x 4608 is four tiles on 148 SMs)
-  const bool few_rows = g.T <= 64 && g.B * g.T <= 128 && 128 % g.T == 0;
+  // (the encoder's GroupNorm+ReLU layers: any T, the samples packed into one tile)
+  const bool few_rows = g.epi == EPI_GN_RELU ? (g.T <= 128 && g.B * g.T <= 128 && g.B <= 128 / g.T)
+                                             : (g.T <= 64 && g.B * g.T <= 128 && 128 % g.T == 0);
   const bool flat = !few_rows && g.epi == EPI_PLAIN && g.B == 1 && g.out_t_stride == 1 && g.T <= 8192;
   if (!few_rows && !flat) return 0;
   long long nkb = 0;
@@ -1263,7 +1392,7 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (ksplit < 2) return 0;
   const int per = (int)((nkb + ksplit - 1) / ksplit);
   ksplit = (int)((nkb + per - 1) / per);             // no empty slice
-  if (g.epi == EPI_GN_MISH && (g.group_width < 8 || g.N % g.group_width != 0 || g.group_width * g.T > 16384)) return 0;
+  if (g.epi != EPI_PLAIN && (g.group_width < 8 || g.N % g.group_width != 0 || g.group_width * g.T > 16384)) return 0;
   if ((size_t)ksplit * rows * g.N * sizeof(float) > SPLITK_SCRATCH_BYTES) return 0;
   if (!ctx->d_splitk) {  // fixed size, allocated once: the pointer is baked into captured graphs
     DT_CUDA(cudaMalloc(&ctx->d_splitk, SPLITK_SCRATCH_BYTES));
@@ -1281,7 +1410,7 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (rc) return rc;
   SplitKEpi e;
   e.part = (const float*)ctx->d_splitk; e.S = ksplit; e.rows = rows; e.T = g.T; e.N = g.N; e.epi = g.epi; e.relu = g.relu;
-  e.gw = (g.epi == EPI_GN_MISH) ? g.group_width : 64;
+  e.gw = (g.epi != EPI_PLAIN) ? g.group_width : 64;
   e.bias = g.bias; e.gamma = g.gamma; e.beta = g.beta; e.film = g.film; e.film_ld = g.film_ld; e.film_t = g.film_t;
   e.resid = g.resid; e.ld_res = g.ld_res; e.out_bf16 = g.out_bf16; e.out_f32 = g.out_f32;
   e.ldc = g.ldc; e.out_b_stride = g.out_b_stride; e.out_t_stride = g.out_t_stride; e.out_off = g.out_off;
@@ -1339,7 +1468,18 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (g.epi == EPI_GN_MISH && g.group_width > 256) return conv_gemm_wide_gn(ctx, g, st);
   // tile geometry: a tile holds whole samples (T <= 128) or a 128-row slice of one sample
   int T = g.T, rows_t, nb, tps;
-  if (T >= BM) {
+  if (g.epi == EPI_GN_RELU || g.a[0].W2 > 0) {
+    // whole samples per tile for ANY T <= 128: floor(128 / T) samples, the rest of the tile stays empty (the
+    // encoder's fused layers, and their split-K partial sums with the plain epilogue: a 2-D source's TMA box is
+    // exactly one sample's output map)
+    if (T < 1 || T > BM) return dt_fail(ctx, DT_E_UNSUPPORTED, "2-D conv source: at most 128 output pixels per sample");
+    if (g.epi == EPI_GN_RELU && (g.group_width != 16 || !g.gamma || !g.beta || !g.out_bf16 || g.out_f32))
+      return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm+ReLU epilogue: groups of 16 channels, bf16 output");
+    if (g.epi == EPI_GN_MISH) return dt_fail(ctx, DT_E_UNSUPPORTED, "2-D conv source with the GroupNorm+Mish epilogue");
+    rows_t = T;
+    nb = BM / T;
+    tps = 0;
+  } else if (T >= BM) {
     if (T % BM != 0 && g.epi == EPI_GN_MISH) return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm epilogue needs T <= 128");
     rows_t = BM;
     nb = 1;
@@ -1357,7 +1497,9 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   }
   if (g.epi == EPI_GN_MISH && T > BM) return dt_fail(ctx, DT_E_UNSUPPORTED, "GroupNorm epilogue needs T <= 128");
   int bn = 256;
-  if (g.epi == EPI_GN_MISH) {
+  if (g.epi == EPI_GN_RELU) {
+    bn = (g.N % 128 == 0) ? 128 : 64;
+  } else if (g.epi == EPI_GN_MISH) {
     const int gw = g.group_width;
     if (gw == 8) bn = 64;
     else if (gw == 16) bn = 128;
@@ -1394,6 +1536,7 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   d.ksplit = g.ksplit > 1 ? g.ksplit : 1;
   d.kb_per_slice = g.ksplit > 1 ? g.kb_per_slice : d.nkb_total;
   d.slice_rows = g.slice_rows;
+  d.a_tile_bytes = rows_t * nb * BK * 2;
 #ifdef GEMM_TIMING
   {
     static int want_n = -2, want_k = 0, want_res = -1;
@@ -1426,6 +1569,10 @@ int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   rc = make_w_map(ctx, &mW, g.w, g.N, g.w_ktot > 0 ? g.w_ktot : ktot, bn / cg);
   if (rc) return rc;
 
+  if (g.epi == EPI_GN_RELU) {
+    if (bn == 128) return launch_gemm<128, EPI_GN_RELU, 16>(ctx, cg, mA0, mA1, mW, d, st);
+    return launch_gemm<64, EPI_GN_RELU, 16>(ctx, cg, mA0, mA1, mW, d, st);
+  }
   if (g.epi == EPI_PLAIN) {
     if (bn == 256) return launch_gemm<256, EPI_PLAIN, 256>(ctx, cg, mA0, mA1, mW, d, st);
     if (bn == 128) return launch_gemm<128, EPI_PLAIN, 128>(ctx, cg, mA0, mA1, mW, d, st);
@@ -1463,6 +1610,44 @@ extern "C" int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M
   g.out_f32 = C;
   g.ldc = N;
   g.out_b_stride = 0;
+  g.out_t_stride = 1;
+  return dt_conv_gemm(ctx, g, (cudaStream_t)stream);
+}
+
+// Test hook for the fused 2-D conv + GroupNorm(16-channel groups) (+ residual) (+ ReLU) launch of the ResNet encoder:
+// in (B, H, W, Cin) bf16 channel-last, Cin % 64 == 0; w [N][k * k * Cin] bf16 (tap-major, then channel); gamma / beta
+// [N] f32; resid (B, OH, OW, N) bf16 or NULL; out (B, OH, OW, N) bf16.  OH * OW <= 128, k * k <= 9.
+extern "C" int dt_conv2d_gn_bf16(dt_ctx* ctx, const void* in, int64_t B, int H, int W, int Cin, const void* w, int N, int k,
+                                 int stride, int pad, const float* gamma, const float* beta, const void* resid, int relu,
+                                 void* out, void* stream) {
+  if (!ctx) return DT_E_ARG;
+  if (!in || !w || !gamma || !beta || !out || B <= 0 || Cin % 64 != 0 || N % 64 != 0 || k < 1 || k * k > GEMM_MAX_SEG ||
+      stride < 1)
+    return dt_fail(ctx, DT_E_ARG, "dt_conv2d_gn_bf16: bad argument");
+  const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+  if (OH < 1 || OW < 1 || OH * OW > BM) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_conv2d_gn_bf16: at most 128 output pixels");
+  ConvGemm g;
+  ActSrc a{(const __nv_bfloat16*)in, Cin, 0, 1};
+  a.W2 = W; a.H2 = H; a.stride2 = stride; a.ow2 = OW; a.oh2 = OH;
+  g.a[0] = a;
+  g.n_src = 1;
+  g.w = (const __nv_bfloat16*)w;
+  g.N = N;
+  g.nseg = 0;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) g.seg[g.nseg++] = GemmSeg{0, kx - pad, ky - pad, Cin / 64, 0};
+  g.B = B;
+  g.T = OH * OW;
+  g.epi = EPI_GN_RELU;
+  g.gamma = gamma;
+  g.beta = beta;
+  g.group_width = 16;
+  g.resid = (const __nv_bfloat16*)resid;
+  g.ld_res = N;
+  g.relu = relu;
+  g.out_bf16 = (__nv_bfloat16*)out;
+  g.ldc = N;
+  g.out_b_stride = OH * OW;
   g.out_t_stride = 1;
   return dt_conv_gemm(ctx, g, (cudaStream_t)stream);
 }

@@ -15,15 +15,22 @@ struct GemmSeg {
               // only ever see zero padding are left out)
 };
 
-#define GEMM_MAX_SEG 8
+#define GEMM_MAX_SEG 9   // a 3 x 3 conv is nine taps
 
-enum { EPI_PLAIN = 0, EPI_GN_MISH = 1 };
+// EPI_GN_RELU (the ResNet encoder): bias -> GroupNorm(groups of 16 channels) -> (+ residual) -> optional ReLU, for ANY
+// number of rows per sample T <= 128 (a tile holds floor(128 / T) whole samples; statistics through shared-memory
+// atomics), so the encoder's 10x10 / 5x5 / 3x3 / 2x2 / 1x1 maps need no separate normalisation kernel.
+enum { EPI_PLAIN = 0, EPI_GN_MISH = 1, EPI_GN_RELU = 3 };
 
 struct ActSrc {
   const __nv_bfloat16* ptr;  // (B, T_in, C) channel-last bf16
   int C;                     // channels (multiple of 64)
   int T_in;                  // time steps per sample in memory
   int P;                     // phase count of the time view (1, or 2 for stride-2 convs)
+  // 2-D source (W2 > 0): ptr is (B, H2, W2, C) channel-last and a tile row is an output pixel (oy, ox) of an
+  // oh2 x ow2 output map read with stride2; a K segment is one conv tap: GemmSeg::phase = kx - pad (x offset),
+  // GemmSeg::t_off = ky - pad (y offset); out-of-range pixels are TMA zero fill = the conv's zero padding
+  int W2 = 0, H2 = 0, stride2 = 1, ow2 = 0, oh2 = 0;
 };
 
 struct ConvGemm {
@@ -49,7 +56,7 @@ struct ConvGemm {
   const float* film_t = nullptr; // per-step (batch-shared) FiLM part [2N], added to `film`
   const __nv_bfloat16* resid = nullptr;  // residual added after the activation, rows like the output
   int64_t ld_res = 0;
-  int relu = 0;                  // EPI_PLAIN only: apply ReLU after bias (+resid)
+  int relu = 0;                  // EPI_PLAIN / EPI_GN_RELU: apply ReLU last (after the residual)
   // ---- output: row (b, t) -> out_row = b*out_b_stride + t*out_t_stride + out_off -----------
   __nv_bfloat16* out_bf16 = nullptr;
   float* out_f32 = nullptr;

@@ -459,6 +459,19 @@ class Context:
                                              self._stream()))
         return out
 
+    def conv2d_gn(self, x, w, gamma, beta, k, stride, pad, resid=None, relu=True):
+        """Test hook: x (B,H,W,Cin) bf16, w (N, k*k*Cin) bf16 tap-major -> (B,OH,OW,N) bf16 (conv -> GroupNorm(N/16) -> +resid -> ReLU)."""
+        assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_contiguous() and w.is_contiguous()
+        B, H, W, Cin = x.shape
+        N = w.shape[0]
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        out = torch.empty((B, OH, OW, N), dtype=torch.bfloat16, device=self.device)
+        ga, be = self._f32(gamma).contiguous(), self._f32(beta).contiguous()
+        self._check(self.lib.dt_conv2d_gn_bf16(self.h, _ptr(x), B, H, W, Cin, _ptr(w), N, int(k), int(stride), int(pad), _ptr(ga),
+                                               _ptr(be), _ptr(resid.contiguous() if resid is not None else None), int(bool(relu)),
+                                               _ptr(out), self._stream()))
+        return out
+
     def gemm_bf16(self, a, w):
         assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
         M, K = a.shape

@@ -314,6 +314,12 @@ int dt_plan_peek_tree(dt_plan* plan, int u, int32_t* n_nodes_out, int32_t* unit_
 /* Test hook for the tcgen05 GEMM core: C[M,N] (f32) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16). */
 int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C, void* stream);
 
+/* Test hook for the encoder's fused launch (local_map_encoder.py:63-76,112-122: a ResNet conv followed by
+ * GroupNorm(C / 16 groups) [+ identity] [+ ReLU]): in (B,H,W,Cin) bf16 channel-last with Cin % 64 == 0, w [N][k*k*Cin]
+ * bf16 (tap-major), gamma / beta [N] f32, resid (B,OH,OW,N) bf16 or NULL, out (B,OH,OW,N) bf16; OH*OW <= 128. */
+int dt_conv2d_gn_bf16(dt_ctx* ctx, const void* in, int64_t B, int H, int W, int Cin, const void* w, int N, int k, int stride,
+                      int pad, const float* gamma, const float* beta, const void* resid, int relu, void* out, void* stream);
+
 /* Per-launch device timing of the tensor-core GEMM kernels (bench.py's roofline): between begin and
  * end every k_conv_gemm launch is bracketed by CUDA events on its own stream.  dt_profile_end
  * synchronises the device and returns the summed kernel time (ms) and the number of launches. */

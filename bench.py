@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--no-suite", action="store_true", help="skip the scenario-suite (scenarios/s) leg")
     ap.add_argument("--suite-runs", type=int, default=40, help="runs per scenario in the suite leg (15 x runs units; the reference's __main__ uses 10: 40 keeps the leg seconds long on 8 GPUs)")
     ap.add_argument("--suite-repeats", type=int, default=3, help="timed repeats of the suite leg (median reported)")
-    ap.add_argument("--suite-unit-slots", type=int, default=8, help="trees grown concurrently per device pass (x 256 edges)")
+    ap.add_argument("--suite-unit-slots", type=int, default=16, help="trees grown concurrently (x 256 edges each), split over --suite-streams plans")
+    ap.add_argument("--suite-streams", type=int, default=2, help="device plans on separate CUDA streams (the short kernels of one overlap the GEMMs of the other)")
     ap.add_argument("--prop-batch", type=int, default=1 << 20, help="candidates for the propagate+collide roofline leg")
     return ap.parse_args()
 
@@ -463,7 +464,7 @@ def main():
         from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
         invalidate_staged_map()
         # the device-resident multi-scenario planner: unit_slots trees x 256 edges per device pass
-        suite_kw = {"unit_slots": args.suite_unit_slots, "iteration_cap": 4096}
+        suite_kw = {"unit_slots": args.suite_unit_slots, "streams": args.suite_streams, "iteration_cap": 4096}
         # untimed warm-up (first-use initialisation of the kernels at this batch size)
         sc.run_suite(sampler, total_runs=1, time_budget=1e9, rank=0, world=1, device=ctx.device,
                      planner_kwargs=dict(suite_kw, iteration_cap=512), engine="device", schedule="static")
@@ -495,7 +496,8 @@ def main():
                  "scenarios_per_s_min": n_units / secs[-1], "scenarios_per_s_max": n_units / secs[0],
                  "repeats": len(secs), "seconds_all": secs,
                  "unit": "one (scenario, run) of test_scenarios_car: RRT on the device-resident multi-scenario planner "
-                         f"({args.suite_unit_slots} trees x 256 edge slots = {args.suite_unit_slots * 256} candidates per device pass), "
+                         f"({args.suite_unit_slots} trees x 256 edge slots in {args.suite_streams} plan(s) on separate streams = "
+                         f"{args.suite_unit_slots * 256 // args.suite_streams} candidates per device pass and plan), "
                          "4096 chunk expansions (the reference's iteration count) or goal, K=1 (the reference's "
                          "planning_diffusion_iters), large denoiser",
                  "engine": "device (csrc/planner.cu): sampling, nearest node, insertion, goal test and path back-trace on "

@@ -25,11 +25,21 @@ from .. import _lib as L
 EDGE_SLOTS = 256
 
 
+class _Plan:
+    """One dt_plan on one device context and stream."""
+    first_done = 0
+    first_done_total = 0
+
+
 class DevicePlanner:
     def __init__(self, sampler, unit_slots=8, iteration_cap=4096, action_horizon=8, prop_duration=(64,),
-                 goal_sample_rate=0.15, goal_conditioning_bias=0.85, local_map_scale=0.2, max_units=256, max_path=4096):
+                 goal_sample_rate=0.15, goal_conditioning_bias=0.85, local_map_scale=0.2, max_units=256, max_path=4096,
+                 streams=1):
         """`sampler`: the DiffusionSampler mirror that owns the packed denoiser (its max_batch should be >=
-        unit_slots * 256); the remaining arguments are RRT_Planner's (planners/RRT.py:19-31)."""
+        unit_slots * 256 / streams); the remaining arguments are RRT_Planner's (planners/RRT.py:19-31).
+        streams = 2 splits the unit slots over two plans on two CUDA streams and two device contexts (same packed
+        weights, own activation arenas): the short kernels at the start and end of one plan's pass (sampling, nearest
+        node, local maps, the first encoder layers, insertion) overlap the other plan's tensor-core phase."""
         self.sampler = sampler
         self.ctx = sampler._context()
         self.lib = self.ctx.lib
@@ -37,8 +47,9 @@ class DevicePlanner:
         self.iteration_cap = int(iteration_cap)
         self.max_units = int(max_units)
         self.max_path = int(max_path)
+        streams = max(1, min(int(streams), self.U))
         cfg = L.PlanCfg()
-        cfg.unit_slots, cfg.edge_slots = self.U, EDGE_SLOTS
+        cfg.edge_slots = EDGE_SLOTS
         cfg.node_cap = self.iteration_cap + 1           # every node costs at least one chunk expansion
         cfg.action_horizon = int(action_horizon)
         sched = [max(1, int(d) // int(action_horizon)) for d in prop_duration][:8]
@@ -52,17 +63,30 @@ class DevicePlanner:
         cfg.local_map_scale = float(local_map_scale)
         for i, v in enumerate(self.ctx._norm_vec(sampler.metadata)):
             cfg.norm[i] = float(v)
-        h = C.c_void_p()
-        self.ctx._check(self.lib.dt_plan_create(self.ctx.h, C.byref(cfg), C.byref(h)))
-        self.h = h
-        self._maps = {}          # maze name -> (slot, rows, cols)
+        self.plans = []
+        for i in range(streams):
+            pl = _Plan()
+            pl.U = self.U // streams + (1 if i < self.U % streams else 0)
+            pl.ctx = self.ctx if i == 0 else sampler._twin_context(pl.U * EDGE_SLOTS)
+            pl.stream = None if streams == 1 else torch.cuda.Stream(device=self.ctx.device)
+            cfg.unit_slots = pl.U
+            h = C.c_void_p()
+            pl.ctx._check(self.lib.dt_plan_create(pl.ctx.h, C.byref(cfg), C.byref(h)))
+            pl.h = h
+            pl.pushed = pl.done = pl.passes = 0
+            pl.maps = {}
+            pl.order = []
+            self.plans.append(pl)
+        self.h = self.plans[0].h
         self._pushed = 0
         self.stats = {}
 
     def close(self):
-        if getattr(self, "h", None):
-            self.lib.dt_plan_destroy(self.h)
-            self.h = None
+        for pl in getattr(self, "plans", []):
+            if pl.h:
+                self.lib.dt_plan_destroy(pl.h)
+                pl.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -71,29 +95,35 @@ class DevicePlanner:
             pass
 
     # ---- maps ----------------------------------------------------------------------------------------------
-    def map_slot(self, name, grid):
-        """Slot of maze `name`, staging it on first use (dt_set_map_slot)."""
-        hit = self._maps.get(name)
+    def _map_slot(self, pl, name, grid):
+        """Slot of maze `name` in plan pl's context, staging it on first use (dt_set_map_slot)."""
+        hit = pl.maps.get(name)
         if hit is None:
-            slot = len(self._maps)
+            slot = len(pl.maps)
             g = np.asarray(grid, dtype=np.float32)
-            self.ctx.set_map_slot(slot, g, 1.0)
-            hit = self._maps[name] = (slot, g.shape[0], g.shape[1])
+            pl.ctx.set_map_slot(slot, g, 1.0)
+            hit = pl.maps[name] = (slot, g.shape[0], g.shape[1])
         return hit
 
+    def _stream_of(self, pl):
+        return torch.cuda.stream(pl.stream) if pl.stream is not None else _NullCtx()
+
     # ---- the loop ------------------------------------------------------------------------------------------
-    def _push(self, units):
+    def _push(self, units, plan=None):
+        pl = self.plans[0] if plan is None else plan
         arr = (L.PlanUnit * len(units))()
         for i, u in enumerate(units):
-            slot, rows, cols = self.map_slot(u["maze_name"], u["maze"])
+            slot, rows, cols = self._map_slot(pl, u["maze_name"], u["maze"])
             for k in range(6):
                 arr[i].start[k] = float(u["start"][k])
             arr[i].goal[0], arr[i].goal[1] = float(u["goal"][0]), float(u["goal"][1])
             arr[i].half_w, arr[i].half_h = cols / 2.0, rows / 2.0   # map_width = len(maze[0]), map_length = len(maze)
             arr[i].map_slot = slot
             arr[i].seed = int(u["seed"]) & 0xFFFFFFFF
-            arr[i].unit_id = self._pushed + i
-        self.ctx._check(self.lib.dt_plan_push(self.h, arr, len(units), self.ctx._stream()))
+            arr[i].unit_id = pl.pushed + i
+        with self._stream_of(pl):
+            pl.ctx._check(self.lib.dt_plan_push(pl.h, arr, len(units), pl.ctx._stream()))
+        pl.pushed += len(units)
         self._pushed += len(units)
 
     def run(self, unit_source, time_budget=None):
@@ -103,70 +133,83 @@ class DevicePlanner:
         collisions, chunks."""
         it = iter(unit_source)
         exhausted = False
-        done = 0
-        first = self._pushed
         t_start = time.perf_counter()
-        pass_times = {}            # plan-wide pass index -> host time at which it was seen complete
         wait_s = 0.0
         counters = (C.c_int32 * 5)()
-        base_pass = int(getattr(self, "_passes", 0))
-        n_pass = 0
+        pull_order = []            # (plan index, unit id inside that plan) in pull order
+        for pl in self.plans:
+            pl.first = pl.pushed
+            pl.base_pass = pl.passes
+            pl.n_pass = 0
+            pl.done = 0
+        pass_times = [dict() for _ in self.plans]   # per plan: pass index -> host time at which it was seen complete
 
         def feed():
             nonlocal exhausted
-            batch = []
-            while not exhausted and (self._pushed + len(batch)) - (first + done) < 2 * self.U:
-                if self._pushed + len(batch) >= self.max_units:
-                    raise RuntimeError(f"DevicePlanner: more than max_units = {self.max_units} units")
-                try:
-                    batch.append(next(it))
-                except StopIteration:
-                    exhausted = True
-            if batch:
-                self._push(batch)
+            for pi, pl in enumerate(self.plans):
+                batch = []
+                while not exhausted and (pl.pushed + len(batch)) - (pl.first + pl.done) < 2 * pl.U:
+                    if pl.pushed + len(batch) >= self.max_units:
+                        raise RuntimeError(f"DevicePlanner: more than max_units = {self.max_units} units per plan")
+                    try:
+                        batch.append(next(it))
+                        pull_order.append((pi, pl.pushed + len(batch) - 1))
+                    except StopIteration:
+                        exhausted = True
+                if batch:
+                    self._push(batch, pl)
 
+        def poll(pi, pl, index):
+            nonlocal wait_s
+            t0 = time.perf_counter()
+            pl.ctx._check(self.lib.dt_plan_counters(pl.h, index, 1, counters))
+            now = time.perf_counter()
+            wait_s += now - t0
+            pass_times[pi][index] = now
+            pl.done = int(counters[2]) - pl.first_done
+            if counters[4] & 1:
+                raise RuntimeError("DevicePlanner: node capacity exhausted")
+
+        for pl in self.plans:
+            pl.first_done = getattr(pl, "first_done_total", 0)
         feed()
-        stream = self.ctx._stream()
         while True:
-            n_units = self._pushed - first
-            if exhausted and done >= n_units:
+            pending = [pl for pl in self.plans if not (exhausted and pl.done >= pl.pushed - pl.first)]
+            if not pending:
                 break
             if time_budget is not None and time.perf_counter() - t_start > time_budget:
                 break
-            self.ctx._check(self.lib.dt_plan_pass(self.h, stream))
-            n_pass += 1
-            if n_pass >= 2:      # one pass stays in flight while the host looks at the one before it
-                t0 = time.perf_counter()
-                self.ctx._check(self.lib.dt_plan_counters(self.h, base_pass + n_pass - 2, 1, counters))
-                now = time.perf_counter()
-                wait_s += now - t0
-                pass_times[base_pass + n_pass - 2] = now
-                done = int(counters[2]) - self._done_before
-                if counters[4] & 1:
-                    raise RuntimeError("DevicePlanner: node capacity exhausted")
-                feed()
-        if n_pass:
-            t0 = time.perf_counter()
-            self.ctx._check(self.lib.dt_plan_counters(self.h, base_pass + n_pass - 1, 1, counters))
-            now = time.perf_counter()
-            wait_s += now - t0
-            pass_times[base_pass + n_pass - 1] = now
-            done = int(counters[2]) - self._done_before
-        self._passes = base_pass + n_pass
-        self._done_before += done
-        self.ctx.sync_status()
+            for pi, pl in enumerate(self.plans):
+                if exhausted and pl.done >= pl.pushed - pl.first:
+                    continue
+                with self._stream_of(pl):
+                    pl.ctx._check(self.lib.dt_plan_pass(pl.h, pl.ctx._stream()))
+                pl.n_pass += 1
+            for pi, pl in enumerate(self.plans):
+                if pl.n_pass >= 2 and (pl.base_pass + pl.n_pass - 2) not in pass_times[pi]:
+                    poll(pi, pl, pl.base_pass + pl.n_pass - 2)   # one pass stays in flight per plan
+            feed()
+        for pi, pl in enumerate(self.plans):
+            if pl.n_pass:
+                poll(pi, pl, pl.base_pass + pl.n_pass - 1)
+            pl.passes = pl.base_pass + pl.n_pass
+            pl.first_done_total = getattr(pl, "first_done_total", 0) + pl.done
+            with self._stream_of(pl):
+                pl.ctx.sync_status()
         wall = time.perf_counter() - t_start
         # results, fetched once
         out = []
         hdr = L.PlanResult()
         path = np.empty((self.max_path, 6), np.float32)
         acts = np.empty((self.max_path, 2), np.float32)
-        for uid in range(first, self._pushed):
-            self.ctx._check(self.lib.dt_plan_fetch(self.h, uid, C.byref(hdr), path.ctypes.data_as(C.c_void_p),
-                                                   acts.ctypes.data_as(C.c_void_p), self.max_path, stream))
+        for pi, uid in pull_order:
+            pl = self.plans[pi]
+            with self._stream_of(pl):
+                pl.ctx._check(self.lib.dt_plan_fetch(pl.h, uid, C.byref(hdr), path.ctypes.data_as(C.c_void_p),
+                                                     acts.ctypes.data_as(C.c_void_p), self.max_path, pl.ctx._stream()))
             finished = hdr.unit_id == uid
-            t1 = pass_times.get(hdr.last_pass, t_start + wall)
-            t0 = pass_times.get(hdr.first_pass - 1, t_start)
+            t1 = pass_times[pi].get(hdr.last_pass, t_start + wall)
+            t0 = pass_times[pi].get(hdr.first_pass - 1, t_start)
             res = {"iterations": int(hdr.iterations) if finished else 0, "number_of_nodes": int(hdr.n_nodes) if finished else 0}
             rec = dict(path=None, actions=None, results=res, runtime=max(t1 - t0, 0.0), finished=bool(finished),
                        goal_reached=bool(hdr.goal_reached) if finished else False,
@@ -177,8 +220,14 @@ class DevicePlanner:
                 rec["actions"] = acts[:hdr.n_actions].copy()
                 res["path_time"] = hdr.n_states * 0.02      # len(path) * env.dt (base_planner.py:237)
             out.append(rec)
-        self.stats = dict(passes=n_pass, wall_s=wall, device_wait_s=wait_s, units=len(out),
-                          candidates_per_pass=self.U * EDGE_SLOTS)
+        self.stats = dict(passes=sum(pl.n_pass for pl in self.plans), wall_s=wall, device_wait_s=wait_s, units=len(out),
+                          candidates_per_pass=self.U * EDGE_SLOTS, streams=len(self.plans))
         return out
 
-    _done_before = 0
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -129,24 +129,32 @@ def gather_rows(local_units, local_rows, n_units_total, device, world, per_rank=
     return table
 
 
+_DESC_CACHE = {}
+
+
 def car_unit_descriptor(row, scenario_idx, run_idx):
     """What the device-resident planner needs to know about one (scenario, run): start / goal exactly as
-    run_car_unit derives them (run_scenarios.py:239-246), the maze and the unit's seed."""
-    from .car_env import CarEnv
-    maze = load_maze(row["maze_name"])
-    env = CarEnv(maze_map=maze, collision_checking=False)
-    start, goal = scenario_states(row, env)
-    # reset() snaps start and goal to their cell centres and sets the heading (base_planner.py:86-90 -> car_env reset)
-    return dict(start=np.asarray(start, dtype=np.float32), goal=np.asarray(env.cell_rowcol_to_xy(
-        env.cell_xy_to_rowcol(goal[:2])), dtype=np.float32), maze=np.float32(maze), maze_name=row["maze_name"],
-        seed=unit_seed(scenario_idx, run_idx), key=(scenario_idx, run_idx))
+    run_car_unit derives them (run_scenarios.py:239-246), the maze and the unit's seed.  The scenario part (an env
+    built once per row to convert its cells) is cached: the runs of a row differ in their seed only."""
+    key = (row["maze_name"], row["start_row"], row["start_col"], row["start_deg"], row["goal_row"], row["goal_col"])
+    hit = _DESC_CACHE.get(key)
+    if hit is None:
+        from .car_env import CarEnv
+        maze = load_maze(row["maze_name"])
+        env = CarEnv(maze_map=maze, collision_checking=False)
+        start, goal = scenario_states(row, env)
+        # reset() snaps the goal to its cell centre (base_planner.py:86-90 -> car_env reset)
+        hit = _DESC_CACHE[key] = dict(start=np.asarray(start, dtype=np.float32), goal=np.asarray(
+            env.cell_rowcol_to_xy(env.cell_xy_to_rowcol(goal[:2])), dtype=np.float32), maze=np.float32(maze),
+            maze_name=row["maze_name"])
+    return dict(hit, seed=unit_seed(scenario_idx, run_idx), key=(scenario_idx, run_idx))
 
 
-def run_suite_device(sampler, units_iter, rows, planner_kwargs=None):
+def run_suite_device(sampler, units_iter, rows, planner_kwargs=None, max_units=4096):
     """Run the units `units_iter` yields ((scenario, run) pairs, possibly from the shared queue) on the device-resident
     multi-scenario planner.  -> (list of (scenario, run), list of result rows, planner stats)."""
     from .planners.device_planner import DevicePlanner
-    kw = dict(unit_slots=8, iteration_cap=4096, max_units=4096)
+    kw = dict(unit_slots=16, streams=2, iteration_cap=4096, max_units=int(max_units))
     kw.update(planner_kwargs or {})
     kw.pop("batch_size", None)
     planner = DevicePlanner(sampler, **kw)
@@ -186,7 +194,7 @@ def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car",
     if engine == "device":
         units = queued_units(all_units(len(rows), total_runs, weights, by_weight=True), world) if queue else \
             shard_units(len(rows), total_runs, rank, world, weights)
-        mine, local, stats = run_suite_device(sampler, units, rows, planner_kwargs)
+        mine, local, stats = run_suite_device(sampler, units, rows, planner_kwargs, max_units=n_total)
         LAST_SUITE_STATS.clear()
         LAST_SUITE_STATS.update(stats)
         table = gather_rows(mine, local, n_total, device, world, per_rank=n_total if queue else None)

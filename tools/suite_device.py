@@ -20,13 +20,14 @@ ap.add_argument("--unit-slots", type=int, default=8)
 ap.add_argument("--denoiser", default="large")
 ap.add_argument("--cap", type=int, default=4096)
 ap.add_argument("--engine", default="device")
+ap.add_argument("--streams", type=int, default=1)
 a = ap.parse_args()
 dims = UNET_DIMS[a.denoiser]
 sd = random_init(seed=0, input_dim=2, cond_dim=7, emb_dim=400, down_dims=dims)
 smp = DiffusionSampler(sd, None, "carmaze", policy="flow_matching", pred_horizon=64, action_dim=2, obs_history=1,
                        action_history=1, goal_conditioned=True, num_diffusion_iters=1, local_map_size=20,
                        max_batch=max(256, a.unit_slots * 256)).eval()
-kw = {"unit_slots": a.unit_slots, "iteration_cap": a.cap} if a.engine == "device" else \
+kw = {"unit_slots": a.unit_slots, "iteration_cap": a.cap, "streams": a.streams} if a.engine == "device" else \
     {"batch_size": 256, "iteration_cap": a.cap}
 # warm-up: one unit
 sc.run_suite(smp, total_runs=1, time_budget=1e9, planner_kwargs=dict(kw, **({"iteration_cap": 512})), engine=a.engine) \

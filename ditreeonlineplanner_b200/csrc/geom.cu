@@ -570,6 +570,129 @@ extern "C" int dt_collide_ant(dt_ctx* ctx, const float* states, int64_t row_stri
   return DT_OK;
 }
 
+// ---- fast variant ------------------------------------------------------------------------------------------
+// The N x N points of a local map are an affine lattice in grid coordinates:
+//     u(i, j) = U0 + i Ui + j Uj   (row coordinate - 0.5),      w(i, j) = W0 + i Wi + j Wj   (column coordinate - 0.5)
+// with six per-pose coefficients, so a point costs two FMAs per coordinate; the nearest integer of a shifted
+// coordinate IS its cell (one magic add, no clamps: the lookup table is the map padded by LM_PAD rings of
+// edge-replicated cells -- numpy's clip -- and already holds the OUTPUT value as a float), and the distance to the
+// cell centre tells whether a cell border is closer than the fp32 error bound `eps`, in which case the float64 code of
+// the reference decides that point.  (i, j) of the pair of points a lane handles in iteration k are the same for
+// every pose: kept in registers.  ~16 instructions per point instead of ~40.
+// Poses whose map can leave the padded table (centre more than a cell outside the map, or a local map wider than the
+// padding) and non-finite poses take the exact code for every point.
+#define LM_PAD 5
+// the reference's float64 decision for one point, out of line (it is needed for ~1 point in 2500: inlined 14 times it
+// quadrupled the kernel and the hot loop missed the instruction cache)
+static __device__ __noinline__ int lm_exact_cell(int rows, int cols, double s, float thf, float pxf, float pyf, double xl,
+                                                 double yl) {
+  MapView m;
+  m.g = nullptr; m.rows = rows; m.cols = cols; m.bytes = 0; m.s = s;
+  double sn, cs;
+  sincos((double)thf, &sn, &cs);
+  const double cx = xmul(xdiv((double)cols, 2.0), s), cy = xmul(xdiv((double)rows, 2.0), s);
+  return local_map_cell_exact(m, cs, sn, (double)pxf, (double)pyf, cx, cy, xl, yl);
+}
+#ifndef LM_MINB
+#define LM_MINB 3
+#endif
+template <typename OutT, bool kMulti, int IT>
+__global__ void __launch_bounds__(GEOM_THREADS, LM_MINB)
+k_local_map_fast(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+                 int64_t stride, int64_t B, int N, Axis ax, OutT* __restrict__ out, MultiMap mm) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ uint64_t bar;
+  if (kMulti) {
+    const int grp = (int)((blockIdx.x * (int64_t)(blockDim.x >> 5)) / mm.group_size);
+    int slot = mm.slot_of_group[grp];
+    slot = (slot < 0 || slot >= DT_MAX_MAP_SLOTS) ? 0 : slot;
+    m = mm.table[slot].m;
+    if (m.g == nullptr) return;
+  }
+  uint8_t* s_map = s_raw;
+  float* s_tab = reinterpret_cast<float*>(s_raw + ((m.bytes + 15) & ~15));
+  dt_stage_map(s_map, &bar, m);
+  const int pitch = m.cols + 2 * LM_PAD, trows = m.rows + 2 * LM_PAD;
+  for (int e = threadIdx.x; e < trows * pitch; e += blockDim.x) {
+    const int r = dt_clampi(e / pitch - LM_PAD, 0, m.rows - 1), c = dt_clampi(e % pitch - LM_PAD, 0, m.cols - 1);
+    const float v = (float)s_map[r * m.cols + c];
+    s_tab[e] = sizeof(OutT) == 4 ? v : v * 2.0f - 1.0f;   // bf16 output: the sampler's rescale (fm_policy.py:152)
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int NN = N * N;
+  // the pair of points (p, p + 1), p = 2 lane + 64 k, of this lane in iteration k
+  float fi[IT], fj[IT];
+  uint32_t wrap = 0;   // bit k: the second point of the pair starts the next row
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int p0 = 2 * lane + 64 * k;
+    const int i = p0 / N, j = p0 - i * N;
+    fi[k] = (float)i;
+    fj[k] = (float)j;
+    wrap |= (j + 1 == N ? 1u : 0u) << k;
+  }
+  const double cx = xmul(xdiv((double)m.cols, 2.0), m.s), cy = xmul(xdiv((double)m.rows, 2.0), m.s);
+  const float inv_s = (float)(1.0 / m.s);
+  const float cxs = (float)(cx / m.s - 0.5), cys = (float)(cy / m.s - 0.5);
+  const float st_s = ax.startf * inv_s, sp_s = ax.stepf * inv_s;
+  const float span = (float)((cx + cy) / m.s) + 2.0f * ax.amax * inv_s;
+  const float MAGIC = 12582912.0f;                       // 1.5 * 2^23: (v + MAGIC) - MAGIC = rint(v)
+  const uint32_t tab_u = dt_smem_u32(s_tab) + 4u * (((uint32_t)LM_PAD - 0x4B400000u) * (uint32_t)(pitch + 1));  // wraps
+  // the lattice stays inside the padded table when the centre is at most one cell outside the map and the local
+  // map's half diagonal (+ the half cell of the shift) fits the rest of the padding
+  const bool reach_ok = 1.4143f * ax.amax * inv_s + 1.6f < (float)LM_PAD;
+  for (int64_t b = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); b < B;
+       b += kMulti ? B : (int64_t)gridDim.x * warps_per_block) {
+    const float pxf = x[b * stride], pyf = y[b * stride], thf = th[b * stride];
+    float snf, csf;
+    const bool th_ok = fabsf(thf) <= DT_SC_MAX;
+    dt_sincos_mufu(th_ok ? thf : 0.f, snf, csf);          // |error| <= DT_SC_ERR (carfast.cuh)
+    const float pxs = pxf * inv_s, pys = pyf * inv_s;
+    const float U0 = cys - pys - (snf + csf) * st_s, Uj = -snf * sp_s, Ui = -csf * sp_s;
+    const float W0 = cxs + pxs + (csf - snf) * st_s, Wj = csf * sp_s, Wi = -snf * sp_s;
+    // fp32 error of a lattice coordinate: <= 16 roundings of magnitude <= |px| + |py| + span (cells), the MUFU
+    // sin / cos error times the lattice radius, doubled for slack
+    const float mag = fabsf(pxs) + fabsf(pys) + span;
+    const float eps = 2.0f * (16.0f * 5.9604645e-8f * mag + 2.0f * DT_SC_ERR * ax.amax * inv_s) + 1.0e-7f;
+    const bool fast_ok = th_ok && reach_ok && eps < 0.25f && fabsf(pxs) <= 0.5f * (float)m.cols + 1.0f &&
+                         fabsf(pys) <= 0.5f * (float)m.rows + 1.0f;
+    const float lim = 0.5f - eps;
+    auto exact_value = [&](int i, int j) -> float {
+      const float v = (float)s_map[lm_exact_cell(m.rows, m.cols, m.s, thf, pxf, pyf, ax.v[j], ax.v[i])];
+      return sizeof(OutT) == 4 ? v : v * 2.0f - 1.0f;
+    };
+    OutT* o = out + b * (int64_t)NN;
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int p0 = 2 * lane + 64 * k;
+      if (p0 < NN) {
+        const bool wr = (wrap >> k) & 1u;
+        const float uA = fmaf(fi[k], Ui, fmaf(fj[k], Uj, U0)), wA = fmaf(fi[k], Wi, fmaf(fj[k], Wj, W0));
+        const float uB = wr ? fmaf(fi[k] + 1.0f, Ui, U0) : uA + Uj, wB = wr ? fmaf(fi[k] + 1.0f, Wi, W0) : wA + Wj;
+        const float tuA = uA + MAGIC, twA = wA + MAGIC, tuB = uB + MAGIC, twB = wB + MAGIC;
+        // distance to the cell centre: beyond 0.5 - eps a border is within the error bound
+        const bool amb = !(fmaxf(fmaxf(fabsf(uA - (tuA - MAGIC)), fabsf(wA - (twA - MAGIC))),
+                                       fmaxf(fabsf(uB - (tuB - MAGIC)), fabsf(wB - (twB - MAGIC)))) < lim);
+        float vA, vB;
+        if (fast_ok && !amb) {
+          const uint32_t aA = tab_u + 4u * (__float_as_uint(tuA) * (uint32_t)pitch + __float_as_uint(twA));
+          const uint32_t aB = tab_u + 4u * (__float_as_uint(tuB) * (uint32_t)pitch + __float_as_uint(twB));
+          asm("ld.shared.f32 %0, [%1];" : "=f"(vA) : "r"(aA));
+          asm("ld.shared.f32 %0, [%1];" : "=f"(vB) : "r"(aB));
+        } else {
+          const int i = p0 / N, j = p0 - i * N;
+          vA = exact_value(i, j);
+          vB = (j + 1 == N) ? exact_value(i + 1, 0) : exact_value(i, j + 1);
+        }
+        if (sizeof(OutT) == 4) *reinterpret_cast<float2*>(o + p0) = make_float2(vA, vB);
+        else *reinterpret_cast<__nv_bfloat162*>(o + p0) = __floats2bfloat162_rn(vA, vB);
+      }
+    }
+  }
+}
+
 // numpy.linspace(start, stop, N): arange(N) * step + start, last element forced to stop
 static Axis make_axis(int N, double scale) {
   Axis ax;
@@ -590,6 +713,38 @@ static Axis make_axis(int N, double scale) {
   return ax;
 }
 
+// -> DT_OK launched, 1 = not applicable (N * N / 64 beyond the instantiated iteration counts), < 0 error
+template <typename OutT, bool kMulti>
+static int local_map_fast_launch_t(dt_ctx* ctx, const MapView& m, const float* x, const float* y, const float* theta,
+                                   int64_t stride, int64_t B, int N, const Axis& ax, OutT* out, const MultiMap& mm,
+                                   int blocks, size_t smem, cudaStream_t st) {
+  const int it = (N * N + 63) / 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done = true;
+  }
+  if (it <= 4) k_local_map_fast<OutT, kMulti, 4><<<blocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, N, ax, out, mm);
+  else if (it <= 7) k_local_map_fast<OutT, kMulti, 7><<<blocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, N, ax, out, mm);
+  else if (it <= 16) k_local_map_fast<OutT, kMulti, 16><<<blocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, N, ax, out, mm);
+  else return 1;
+  DT_LAUNCH_CHECK("k_local_map_fast");
+  return DT_OK;
+}
+
+static int local_map_fast_launch(dt_ctx* ctx, const MapView& m, const float* x, const float* y, const float* theta,
+                                 int64_t stride, int64_t B, int N, const Axis& ax, int out_dtype, void* out,
+                                 const MultiMap& mm, int blocks, size_t smem, cudaStream_t st) {
+  if (mm.table) {
+    return local_map_fast_launch_t<__nv_bfloat16, true>(ctx, m, x, y, theta, stride, B, N, ax, (__nv_bfloat16*)out, mm, blocks, smem, st);
+  }
+  if (out_dtype == DT_F32)
+    return local_map_fast_launch_t<float, false>(ctx, m, x, y, theta, stride, B, N, ax, (float*)out, mm, blocks, smem, st);
+  return local_map_fast_launch_t<__nv_bfloat16, false>(ctx, m, x, y, theta, stride, B, N, ax, (__nv_bfloat16*)out, mm, blocks, smem, st);
+}
+
 extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const float* theta, int64_t stride, int64_t B,
                             int N, double scale, int out_dtype, void* out, void* stream) {
   NEED_MAP();
@@ -602,18 +757,22 @@ extern "C" int dt_local_map(dt_ctx* ctx, const float* x, const float* y, const f
   int64_t blocks = (B + warps - 1) / warps;
   if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
   cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype != DT_F32 && out_dtype != DT_BF16) return dt_fail(ctx, DT_E_ARG, "dt_local_map: unknown out_dtype");
   // paired points (packed 8- / 4-byte stores) need an even point count per pose and an aligned output
   const int even = ((N * N) & 1) == 0;
+  const int pair = even && (reinterpret_cast<uintptr_t>(out) & (out_dtype == DT_F32 ? 7u : 3u)) == 0;
+  const size_t tab_bytes = (size_t)((m.bytes + 15) & ~15) + (size_t)(m.rows + 2 * LM_PAD) * (m.cols + 2 * LM_PAD) * 4;
+  if (pair && tab_bytes <= 96 * 1024) {
+    const MultiMap none{nullptr, nullptr, 0};
+    int rc = local_map_fast_launch(ctx, m, x, y, theta, stride, B, N, ax, out_dtype, out, none, (int)blocks, tab_bytes, st);
+    if (rc != 1) return rc;
+  }
   if (out_dtype == DT_F32) {
-    const int pair = even && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
     k_local_map<float, false><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(m, x, y, theta, stride, B, N, ax, pair,
                                                                             (float*)out, MultiMap{nullptr, nullptr, 0});
-  } else if (out_dtype == DT_BF16) {
-    const int pair = even && (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+  } else {
     k_local_map<__nv_bfloat16, false><<<(int)blocks, GEOM_THREADS, m.bytes, st>>>(
         m, x, y, theta, stride, B, N, ax, pair, (__nv_bfloat16*)out, MultiMap{nullptr, nullptr, 0});
-  } else {
-    return dt_fail(ctx, DT_E_ARG, "dt_local_map: unknown out_dtype");
   }
   DT_LAUNCH_CHECK("k_local_map");
   return DT_OK;
@@ -636,9 +795,23 @@ extern "C" int dt_local_map_slots(dt_ctx* ctx, const float* x, const float* y, c
   const int pair = (((N * N) & 1) == 0) && (reinterpret_cast<uintptr_t>(out_bf16) & 3u) == 0;
   const int64_t blocks = B / warps;
   if (blocks > 0x7fffffffLL) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_local_map_slots: batch too large");
+  const MultiMap mm{(const MapEntry*)ctx->d_map_table, slot_of_group, group_size};
+  // the largest staged slot decides the shared memory of every block
+  int max_cells = 0, max_tab = 0;
+  for (const dt_map_slot& sl : ctx->slots) {
+    if (!sl.d_map) continue;
+    if (sl.map_bytes > max_cells) max_cells = sl.map_bytes;
+    const int t = (sl.rows + 2 * LM_PAD) * (sl.cols + 2 * LM_PAD) * 4;
+    if (t > max_tab) max_tab = t;
+  }
+  const size_t tab_bytes = (size_t)((max_cells + 15) & ~15) + (size_t)max_tab;
+  if (pair && tab_bytes <= 96 * 1024) {
+    int rc = local_map_fast_launch(ctx, none, x, y, theta, stride, B, N, ax, DT_BF16, out_bf16, mm, (int)blocks, tab_bytes,
+                                   (cudaStream_t)stream);
+    if (rc != 1) return rc;
+  }
   k_local_map<__nv_bfloat16, true><<<(int)blocks, GEOM_THREADS, ((ctx->slots_max_bytes + 15) / 16) * 16, (cudaStream_t)stream>>>(
-      none, x, y, theta, stride, B, N, ax, pair, (__nv_bfloat16*)out_bf16,
-      MultiMap{(const MapEntry*)ctx->d_map_table, slot_of_group, group_size});
+      none, x, y, theta, stride, B, N, ax, pair, (__nv_bfloat16*)out_bf16, mm);
   DT_LAUNCH_CHECK("k_local_map(slots)");
   return DT_OK;
 }

@@ -149,13 +149,15 @@ class DevicePlanner:
             for pi, pl in enumerate(self.plans):
                 batch = []
                 while not exhausted and (pl.pushed + len(batch)) - (pl.first + pl.done) < 2 * pl.U:
-                    if pl.pushed + len(batch) >= self.max_units:
-                        raise RuntimeError(f"DevicePlanner: more than max_units = {self.max_units} units per plan")
                     try:
-                        batch.append(next(it))
-                        pull_order.append((pi, pl.pushed + len(batch) - 1))
+                        unit = next(it)
                     except StopIteration:
                         exhausted = True
+                        break
+                    if pl.pushed + len(batch) >= self.max_units:
+                        raise RuntimeError(f"DevicePlanner: more than max_units = {self.max_units} units per plan")
+                    batch.append(unit)
+                    pull_order.append((pi, pl.pushed + len(batch) - 1))
                 if batch:
                     self._push(batch, pl)
 

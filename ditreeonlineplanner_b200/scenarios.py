@@ -194,7 +194,7 @@ def run_suite(sampler, total_runs=1, time_budget=5.0, kind="test_scenarios_car",
     if engine == "device":
         units = queued_units(all_units(len(rows), total_runs, weights, by_weight=True), world) if queue else \
             shard_units(len(rows), total_runs, rank, world, weights)
-        mine, local, stats = run_suite_device(sampler, units, rows, planner_kwargs, max_units=n_total)
+        mine, local, stats = run_suite_device(sampler, units, rows, planner_kwargs, max_units=n_total + 1)
         LAST_SUITE_STATS.clear()
         LAST_SUITE_STATS.update(stats)
         table = gather_rows(mine, local, n_total, device, world, per_rank=n_total if queue else None)

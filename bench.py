@@ -468,11 +468,14 @@ def main():
         # untimed warm-up (first-use initialisation of the kernels at this batch size)
         sc.run_suite(sampler, total_runs=1, time_budget=1e9, rank=0, world=1, device=ctx.device,
                      planner_kwargs=dict(suite_kw, iteration_cap=512), engine="device", schedule="static")
+        # enough units that a repeat lasts seconds on every GPU count (>= 5 s at 8 GPUs): 600 units up to 2 GPUs,
+        # 1200 at 4, 2400 at 8; throughput is per unit, so the figures of different GPU counts compare directly
+        suite_runs = args.suite_runs * max(1, world // 2)
         reps = []
         for rep in range(args.suite_repeats):
             barrier()
             t0 = time.perf_counter()
-            table, _ = sc.run_suite(sampler, total_runs=args.suite_runs, time_budget=1e9, rank=rank, world=world,
+            table, _ = sc.run_suite(sampler, total_runs=suite_runs, time_budget=1e9, rank=rank, world=world,
                                     device=ctx.device, planner_kwargs=suite_kw, engine="device")
             barrier()
             t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)

@@ -756,6 +756,21 @@ extern "C" int dt_load_denoiser(dt_ctx* ctx, const dt_tensor_desc* tensors, int 
   for (int i = 0; i < 4; ++i) d->e[i] = arena<bf>(d, MB * (size_t)oh1 * oh1 * 64, &aok);
   d->emb = arena<float>(d, MB * d->emb_pad, &aok);
   d->lin = arena<float>(d, MB * d->emb_pad, &aok);
+  // GroupNorm groups wider than one N tile (`xlarge`: 4096 / 8 = 512 channels) take the unfused path through an
+  // fp32 scratch of the largest such layer (gemm.cu, conv_gemm_wide_gn): sized here, once, so that no launch path
+  // ever allocates or synchronises (and stays graph-capturable)
+  {
+    size_t wide = 0;
+    for (int l = 0; l < 3; ++l)
+      if (C[l] / 8 > 256) wide = std::max(wide, MB * (size_t)d->Tl[l] * C[l] * sizeof(float));
+    if (wide > ctx->wide_bytes) {
+      if (ctx->d_wide) cudaFree(ctx->d_wide);
+      ctx->d_wide = nullptr;
+      ctx->wide_bytes = 0;
+      if (cudaMalloc(&ctx->d_wide, wide) == cudaSuccess) ctx->wide_bytes = wide;
+      else aok = false;
+    }
+  }
   if (!aok) {
     dt_denoiser_free(ctx);
     return dt_fail(ctx, DT_E_CUDA, "dt_load_denoiser: out of device memory for scratch (lower max_batch)");

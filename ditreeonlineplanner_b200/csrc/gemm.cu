@@ -1203,14 +1203,8 @@ static int conv_gemm_wide_gn(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (g.N % g.group_width != 0 || !g.gamma || !g.beta || !g.out_bf16)
     return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad wide GroupNorm problem");
   const size_t need = (size_t)g.B * g.T * g.N * sizeof(float);
-  if (need > ctx->wide_bytes) {
-    DT_CUDA(cudaStreamSynchronize(st));
-    if (ctx->d_wide) DT_CUDA(cudaFree(ctx->d_wide));
-    ctx->d_wide = nullptr;
-    ctx->wide_bytes = 0;
-    DT_CUDA(cudaMalloc(&ctx->d_wide, need));
-    ctx->wide_bytes = need;
-  }
+  if (need > ctx->wide_bytes)   // sized by dt_load_denoiser for max_batch; callers chunk larger batches
+    return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: wide GroupNorm scratch too small (batch beyond the loaded max_batch)");
   ConvGemm plain = g;
   plain.epi = EPI_PLAIN;
   plain.gamma = plain.beta = nullptr;

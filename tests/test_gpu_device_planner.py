@@ -172,3 +172,27 @@ def test_distribution_matches_host_planners(sampler, mazes):
     msg = f"B = 1 loop {b1_nodes:.4f} vs device (8 passes) {dev_nodes:.4f} nodes per chunk expansion"
     print(msg)
     assert abs(dev_nodes - b1_nodes) <= 0.4 * max(dev_nodes, b1_nodes), msg
+
+
+def test_goal_reached_in_flight(sampler, mazes):
+    """A unit that starts 0.7 m from its goal, rolling towards it at 3 m/s, enters the goal disc within its first chunk
+    whatever the sampler proposes: goal detection, the edge's truncation at the goal step, the final-node choice and the
+    path copy-out of the goal branch (RRT.py:208-219), next to a unit that runs to its iteration cap in the same passes."""
+    from ditreeonlineplanner_b200.planners.device_planner import DevicePlanner
+    far = _units([0], 1)[0]
+    near = dict(far)
+    g = np.asarray(far["goal"], dtype=np.float32)
+    near["start"] = np.array([g[0] - 0.7, g[1], 0.0, 3.0, 0.5, 0.0], dtype=np.float32)
+    near["seed"] = 12345
+    pl = DevicePlanner(sampler, unit_slots=2, iteration_cap=768, max_units=8)
+    recs = pl.run(iter([near, far]))
+    pl.close()
+    r = recs[0]
+    assert r["finished"] and r["goal_reached"] and r["error"] == 0
+    assert r["results"]["iterations"] == 256               # found in the first pass
+    end = _replay(r, near)
+    assert np.linalg.norm(end[:2] - g) < 0.5
+    assert 2 <= len(r["actions"]) <= 8                      # one truncated chunk
+    # the state before the last one was still outside the disc (the edge stops AT the goal step)
+    assert np.linalg.norm(r["path"][-3, :2].astype(np.float64) - g) >= 0.5 or len(r["actions"]) == 1
+    assert recs[1]["finished"] and not recs[1]["goal_reached"] and recs[1]["results"]["iterations"] == 768

@@ -8,7 +8,8 @@ weights of the reference architecture) -> 50-step bicycle rollout fused with gri
 (sample + propagate + collide).
 
     python bench.py --gpus N --steps K --warmup W          # our arm (torchrun for N > 1)
-    python bench.py --impl reference ...                   # the reference's CPU path (oracle port)
+    python bench.py --impl reference ...                   # the UNMODIFIED reference on the host cores (oracle/_ref, staged by
+                                                           # oracle/build_ref.py; the oracle port only when that is missing)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
@@ -108,7 +109,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-# the reference's CPU path (oracle port): same pipeline, bounded sample
+# the reference's CPU path: the staged unmodified reference (or the oracle port), same pipeline, bounded sample
 # ---------------------------------------------------------------------------------------------
 CPU_SAMPLE = 64  # candidates per CPU step: fixed, independent of --steps (a 9-candidate step ran torch-CPU convs at 40 %
                  # of the throughput of a 64-candidate one and inflated the GPU / CPU ratio)

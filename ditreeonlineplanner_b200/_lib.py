@@ -31,12 +31,12 @@ class PlanCfg(C.Structure):
                 ("n_sched", C.c_int32), ("sched_chunks", C.c_int32 * 8), ("iteration_cap", C.c_int32),
                 ("ode_steps", C.c_int32), ("max_units", C.c_int32), ("max_path", C.c_int32),
                 ("goal_sample_rate", C.c_float), ("goal_conditioning_bias", C.c_float),
-                ("local_map_scale", C.c_double), ("norm", C.c_double * 16)]
+                ("local_map_scale", C.c_double), ("norm", C.c_double * 16), ("run_type", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PlanUnit(C.Structure):
     _fields_ = [("start", C.c_float * 6), ("goal", C.c_float * 2), ("half_w", C.c_float), ("half_h", C.c_float),
-                ("map_slot", C.c_int32), ("seed", C.c_uint32), ("unit_id", C.c_int32), ("reserved", C.c_int32)]
+                ("map_slot", C.c_int32), ("seed", C.c_uint32), ("unit_id", C.c_int32), ("cdf_slot", C.c_int32)]
 
 
 class PlanResult(C.Structure):
@@ -58,6 +58,8 @@ SIGNATURES = {
     "dt_plan_destroy": (None, [c_p]),
     "dt_plan_push": (C.c_int, [c_p, C.POINTER(PlanUnit), C.c_int, c_p]),
     "dt_plan_pass": (C.c_int, [c_p, c_p]),
+    "dt_plan_set_cdf": (C.c_int, [c_p, C.c_int, c_p, C.c_int, c_p]),
+    "dt_plan_peek_slots": (C.c_int, [c_p, c_p, c_p, c_p]),
     "dt_plan_counters": (C.c_int, [c_p, c_i64, C.c_int, C.POINTER(C.c_int32)]),
     "dt_plan_fetch": (C.c_int, [c_p, C.c_int, C.POINTER(PlanResult), c_p, c_p, C.c_int, c_p]),
     "dt_plan_peek_tree": (C.c_int, [c_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_p, c_p, C.c_int, c_p]),

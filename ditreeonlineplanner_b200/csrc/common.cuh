@@ -210,6 +210,28 @@ __device__ __forceinline__ int dt_ball_test(const uint8_t* __restrict__ grid, in
   return hit | err;
 }
 
+// check_obstacle_ahead (planners/RRT.py:61-81) for one state: 30 samples on linspace(0, 1.5) along
+// (cos(-theta), sin(-theta)) from the robot's un-floored (col, row); truncation toward zero, clip, any wall.
+__device__ __forceinline__ int dt_ray_probe_one(const uint8_t* __restrict__ grid, int R, int C, float xf, float yf,
+                                                float thf) {
+  const double cx = xdiv((double)C, 2.0), cy = xdiv((double)R, 2.0);  // the env's cell size is 1 for the car
+  const double step = xdiv(1.5, 29.0);
+  const double row = xsub(cy, (double)yf);
+  const double col = xadd((double)xf, cx);
+  double sn, cs;
+  sincos(-(double)thf, &sn, &cs);
+  int hit = 0;
+  for (int k = 0; k < 30; ++k) {
+    const double t = (k == 29) ? 1.5 : xmul((double)k, step);
+    const double sx = xadd(xmul(t, cs), col), sy = xadd(xmul(t, sn), row);
+    int qx = (int)sx, qy = (int)sy;  // astype('int'): truncation toward zero
+    qx = dt_clampi(qx, 0, C - 1);
+    qy = dt_clampi(qy, 0, R - 1);
+    hit |= (grid[qy * C + qx] != 0);
+  }
+  return hit;
+}
+
 // is_colliding_car (common/map_utils.py:103-115) on a float32 state up-cast to float64.
 // Returns 0/1, or 1|4 when the reference would raise.
 __device__ __forceinline__ int dt_car_test(const uint8_t* __restrict__ grid, int R, int C, float xf, float yf,

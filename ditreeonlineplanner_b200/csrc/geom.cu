@@ -324,23 +324,8 @@ k_ray_probe(MapView m, const float* __restrict__ x, const float* __restrict__ y,
   extern __shared__ __align__(16) uint8_t s_map[];
   __shared__ uint64_t bar;
   dt_stage_map(s_map, &bar, m);
-  // the env's cell size is 1 for the car (car_env.py:82)
-  const double cx = xdiv((double)m.cols, 2.0), cy = xdiv((double)m.rows, 2.0);
-  const double step = xdiv(1.5, 29.0);  // linspace(0, 1.5, 30)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
-    const double row = xsub(cy, (double)y[i * stride]);
-    const double col = xadd((double)x[i * stride], cx);
-    double sn, cs;
-    sincos(-(double)th[i * stride], &sn, &cs);
-    int hit = 0;
-    for (int k = 0; k < 30; ++k) {
-      const double t = (k == 29) ? 1.5 : xmul((double)k, step);
-      const double sx = xadd(xmul(t, cs), col), sy = xadd(xmul(t, sn), row);
-      int qx = (int)sx, qy = (int)sy;  // astype('int'): truncation toward zero
-      qx = dt_clampi(qx, 0, m.cols - 1);
-      qy = dt_clampi(qy, 0, m.rows - 1);
-      hit |= (s_map[qy * m.cols + qx] != 0);
-    }
+    const int hit = dt_ray_probe_one(s_map, m.rows, m.cols, x[i * stride], y[i * stride], th[i * stride]);
     out[i] = (uint8_t)hit;
   }
 }

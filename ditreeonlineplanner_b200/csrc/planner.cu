@@ -26,8 +26,10 @@
 // The host only enqueues passes and reads a few counters with a lag; no device->host copy sits between the passes.
 // Deviations from the reference loop, all inherited from the batched planner (planners/RRT.py docstring): the S
 // samples of a pass see the tree as of the start of the pass; random numbers come from per-unit Philox streams, not
-// from the three host generators.  run_type 0 only (uniform state sampler); other run types use the host-driven
-// planners.
+// from the three host generators.  run_type 0 (uniform state sampler) and run_types 1-3 without a previous main path
+// (probability-map cell sampler for run_type >= 2 -- np.random.choice over the unit's CDF, dt_plan_set_cdf --, the
+// sample as conditioning goal, the obstacle-ahead probe per new node and its penalty in the final selection); replans
+// along a previous main path (the online driver) use the host-driven planners.
 #include <cooperative_groups.h>
 
 #include "carprop.cuh"
@@ -38,6 +40,7 @@ extern "C" int dt_local_map_slots(dt_ctx* ctx, const float* x, const float* y, c
 
 #define PLAN_MAX_SCHED 8
 #define PLAN_MAX_DEPTH 1024      // longest root-to-leaf chain the path copy-out handles
+#define PLAN_MAX_CDF 64          // probability maps (their CDFs) staged at once
 #define PLAN_THREADS_REFILL 256
 
 enum { CNT_HEAD = 0, CNT_TAIL = 1, CNT_DONE = 2, CNT_PASS = 3, CNT_ERR = 4, CNT_ACTIVE = 5, CNT_N = 8 };
@@ -48,12 +51,16 @@ struct PlanUnit {   // one unit slot (device)
   int map_slot;
   uint32_t seed;
   int n_nodes, passes, first_pass, fresh;
+  int cdf_slot;     // probability-map sampler (run_type >= 2): slot of the unit's CDF, -1 = uniform sampler
   float goal[2], half_w, half_h;
   int chunks, collisions;   // statistics: chunk expansions booked / chunks that ended in a collision
 };
 
 struct PlanDev {   // everything the kernels need, by value
-  int U, S, ncap, h, nmax, T, A, erec, max_path, max_units, iter_cap, n_sched;
+  int U, S, ncap, h, nmax, T, A, erec, max_path, max_units, iter_cap, n_sched, run_type;
+  const double* cdf;              // [PLAN_MAX_CDF][DT_MAX_MAP_CELLS] normalised cumulative sums
+  const int* cdf_n;               // cells per slot
+  uint8_t* node_ahead;            // check_obstacle_ahead of every node (run_type >= 1)
   int sched[PLAN_MAX_SCHED];      // chunks per edge by visit count of the parent (prop_duration // action_horizon)
   float goal_sample_rate, goal_cond_bias;
   float act_mean[2];
@@ -150,9 +157,31 @@ k_plan_refill(PlanDev p) {
   // conditioning goal (RRT.py:154-157): the sample with probability 1 - goal_conditioning_bias, else the goal
   const uint4 r = philox4x32(make_uint4((uint32_t)sl, (uint32_t)un.passes, 0u, 2u), key);
   const bool explore = u01(r.x) > p.goal_sample_rate;
-  const float sx = explore ? fmaf(2.0f * un.half_w, u01(r.y), -un.half_w) : un.goal[0];
-  const float sy = explore ? fmaf(2.0f * un.half_h, u01(r.z), -un.half_h) : un.goal[1];
-  const bool cond_sample = u01(r.w) > p.goal_cond_bias;
+  float sx = un.goal[0], sy = un.goal[1];
+  if (explore) {
+    if (un.cdf_slot >= 0) {
+      // sample_row_col_from_probability_map (base_planner.py:157-160): np.random.choice(size, p = prob_map) =
+      // searchsorted(cdf, u, side = 'right') with a 53-bit uniform variate, then the cell's centre
+      // (cell_rowcol_to_xy, car_env.py:189-194)
+      const double uu = ((double)(r.y >> 5) * 67108864.0 + (double)(r.z >> 6)) * (1.0 / 9007199254740992.0);
+      const double* cdf = p.cdf + (size_t)un.cdf_slot * DT_MAX_MAP_CELLS;
+      int lo = 0, hi = p.cdf_n[un.cdf_slot];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      const int cols = (int)(2.0f * un.half_w + 0.5f);
+      const int cell = lo < p.cdf_n[un.cdf_slot] ? lo : p.cdf_n[un.cdf_slot] - 1;
+      const int row = cell / cols, col = cell - row * cols;
+      sx = ((float)col + 0.5f) - un.half_w;
+      sy = un.half_h - ((float)row + 0.5f);
+    } else {
+      sx = fmaf(2.0f * un.half_w, u01(r.y), -un.half_w);
+      sy = fmaf(2.0f * un.half_h, u01(r.z), -un.half_h);
+    }
+  }
+  // run_type 0: the sample with probability 1 - goal_conditioning_bias, else the goal; other run types: the sample
+  const bool cond_sample = p.run_type != 0 || u01(r.w) > p.goal_cond_bias;
   // nearest node (RRT.py:49-55): KDTree.query on (x, y); squared distances in float64, lowest index on ties
   const float* nx = p.node_x + (size_t)u * p.ncap;
   const float* ny = p.node_y + (size_t)u * p.ncap;
@@ -213,6 +242,8 @@ __device__ __forceinline__ void plan_start_unit(const PlanDev& p, int u, const d
   un.goal[1] = d.goal[1];
   un.half_w = d.half_w;
   un.half_h = d.half_h;
+  un.cdf_slot = (p.run_type >= 2 && d.cdf_slot >= 0 && d.cdf_slot < PLAN_MAX_CDF) ? d.cdf_slot : -1;
+  p.node_ahead[root] = 0;
   un.chunks = 0;
   un.collisions = 0;
   p.unit_slot_map[u] = d.map_slot;
@@ -331,6 +362,8 @@ k_plan_advance(PlanDev p, int* __restrict__ status) {
     p.node_lastact[node * 2 + 1] = last_u1;
     p.node_len[node * 2] = len_s;
     p.node_len[node * 2 + 1] = len_a;
+    // has_obstacle_ahead of the new node (RRT.py:201-205): always False for run_type 0
+    p.node_ahead[node] = p.run_type == 0 ? 0 : (uint8_t)dt_ray_probe_one(s_map, m.rows, m.cols, c.x, c.y, c.psi);
     if (done) atomicMin(&s_goal_slot, tid);
   }
   // the edge records of the new nodes: warp-cooperative copies (coalesced), one ending slot at a time
@@ -381,18 +414,24 @@ k_plan_advance(PlanDev p, int* __restrict__ status) {
   const float* ny = p.node_y + (size_t)u * p.ncap;
   int final_node = s_goal_node;
   if (final_node < 0) {
-    // arg-min over the nodes but the root of ||p - goal|| (float64, first index on ties); run_type 0 has no
-    // obstacle-ahead penalty.  No node but the root: np.all([]) is True and the reference returns (None, None).
+    // arg-min over the nodes but the root of ||p - goal|| + 1e4 * obstacle_ahead (float64, first index on ties,
+    // RRT.py:233-237).  No node but the root, or an obstacle ahead of every node: np.all(has_obstacle_ahead) is True
+    // and the reference returns (None, None) (:221-226).
+    const uint8_t* ahead = p.node_ahead + (size_t)u * p.ncap;
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int bi = 0x7fffffff;
+    int any_clear = 0;
     for (int j = 1 + tid; j < n_nodes; j += blockDim.x) {
       const double dx = xsub((double)nx[j], (double)s_un.goal[0]), dy = xsub((double)ny[j], (double)s_un.goal[1]);
-      const double d = __dsqrt_rn(xadd(xmul(dx, dx), xmul(dy, dy)));
+      double d = __dsqrt_rn(xadd(xmul(dx, dx), xmul(dy, dy)));
+      if (ahead[j]) d = xadd(d, xmul(10e3, 1.0));
+      else any_clear = 1;
       if (d < best) {
         best = d;
         bi = j;
       }
     }
+    if (!__syncthreads_or(any_clear)) bi = 0x7fffffff;
     plan_warp_argmin(best, bi);
     if (lane == 0) {
       s_bd[warp] = best;
@@ -530,7 +569,8 @@ extern "C" int dt_plan_create(dt_ctx* ctx, const dt_plan_cfg* cfg, dt_plan** out
   if (cfg->unit_slots < 1 || cfg->unit_slots > 64 || cfg->edge_slots != 256)
     return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_plan_create: 1..64 unit slots of exactly 256 edge slots");
   if (cfg->action_horizon < 1 || cfg->action_horizon > mc.horizon || cfg->n_sched < 1 || cfg->n_sched > PLAN_MAX_SCHED ||
-      cfg->node_cap < 2 || cfg->max_units < 1 || cfg->max_path < 16 || cfg->ode_steps < 1 || mc.action_dim != 2)
+      cfg->node_cap < 2 || cfg->max_units < 1 || cfg->max_path < 16 || cfg->ode_steps < 1 || mc.action_dim != 2 ||
+      cfg->run_type < 0 || cfg->run_type > 3)
     return dt_fail(ctx, DT_E_ARG, "dt_plan_create: bad configuration");
   DT_CUDA(cudaSetDevice(ctx->device));
   dt_plan* pl = new dt_plan();
@@ -541,6 +581,7 @@ extern "C" int dt_plan_create(dt_ctx* ctx, const dt_plan_cfg* cfg, dt_plan** out
   d.U = cfg->unit_slots; d.S = cfg->edge_slots; d.ncap = cfg->node_cap; d.h = cfg->action_horizon;
   d.T = mc.horizon; d.A = mc.action_dim; d.max_path = cfg->max_path; d.max_units = cfg->max_units;
   d.iter_cap = cfg->iteration_cap; d.n_sched = cfg->n_sched;
+  d.run_type = cfg->run_type;
   d.nmax = 1;
   for (int i = 0; i < cfg->n_sched; ++i) {
     d.sched[i] = cfg->sched_chunks[i];
@@ -567,6 +608,15 @@ extern "C" int dt_plan_create(dt_ctx* ctx, const dt_plan_cfg* cfg, dt_plan** out
   PA(d.node_x, NN); PA(d.node_y, NN); PA(d.node_state, NN * 6); PA(d.node_lastact, NN * 2);
   PA(d.node_edge, NN * d.erec);
   PA(d.node_parent, NN); PA(d.node_visit, NN); PA(d.node_len, NN * 2);
+  PA(d.node_ahead, NN);
+  if (cfg->run_type >= 2) {
+    double* cdf = nullptr;
+    int* cdf_n = nullptr;
+    PA(cdf, (size_t)PLAN_MAX_CDF * DT_MAX_MAP_CELLS);
+    PA(cdf_n, (size_t)PLAN_MAX_CDF);
+    d.cdf = cdf;
+    d.cdf_n = cdf_n;
+  }
   PA(d.slot_state, P * 6); PA(d.slot_prev, P * 2); PA(d.slot_goal, P * 2); PA(d.slot_edge, P * d.erec);
   PA(d.slot_parent, P); PA(d.slot_chunk, P); PA(d.slot_nchunks, P); PA(d.slot_free, P);
   PA(d.noise, P * d.T * d.A); PA(d.actions, P * d.T * d.A);
@@ -606,6 +656,8 @@ extern "C" int dt_plan_push(dt_plan* pl, const dt_plan_unit* units_host, int n, 
         ctx->slots[un.map_slot].d_map == nullptr)
       return dt_fail(ctx, DT_E_ARG, "dt_plan_push: bad unit id or map slot not staged (dt_set_map_slot)");
     if (ctx->slots[un.map_slot].s_global != 1.0) return dt_fail(ctx, DT_E_UNSUPPORTED, "dt_plan_push: car maps use 1 m cells");
+    if (pl->d.run_type >= 2 && (un.cdf_slot < 0 || un.cdf_slot >= PLAN_MAX_CDF))
+      return dt_fail(ctx, DT_E_ARG, "dt_plan_push: run_type >= 2 needs the unit's probability map (dt_plan_set_cdf slot)");
   }
   cudaStream_t st = (cudaStream_t)stream;
   pl->d.table = (const MapEntry*)ctx->d_map_table;
@@ -618,6 +670,42 @@ extern "C" int dt_plan_push(dt_plan* pl, const dt_plan_unit* units_host, int n, 
   DT_CUDA(cudaStreamSynchronize(st));
   k_plan_fill_idle<<<pl->d.U, 256, 0, st>>>(pl->d);
   DT_LAUNCH_CHECK("k_plan_fill_idle");
+  return DT_OK;
+}
+
+extern "C" int dt_plan_set_cdf(dt_plan* pl, int slot, const double* prob_host, int n, void* stream) {
+  if (!pl) return DT_E_ARG;
+  dt_ctx* ctx = pl->ctx;
+  if (!pl->d.cdf) return dt_fail(ctx, DT_E_ARG, "dt_plan_set_cdf: the plan was created with run_type < 2");
+  if (slot < 0 || slot >= PLAN_MAX_CDF || !prob_host || n < 1 || n > DT_MAX_MAP_CELLS)
+    return dt_fail(ctx, DT_E_ARG, "dt_plan_set_cdf: bad slot or size");
+  // RandomState.choice: cdf = p.cumsum(); cdf /= cdf[-1]  (sequential float64 sums, as NumPy does them)
+  std::vector<double> cdf((size_t)n);
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (!(prob_host[i] >= 0.0)) return dt_fail(ctx, DT_E_ARG, "dt_plan_set_cdf: probabilities are not non-negative");
+    acc += prob_host[i];
+    cdf[i] = acc;
+  }
+  if (!(acc > 0.0)) return dt_fail(ctx, DT_E_ARG, "dt_plan_set_cdf: probabilities sum to zero");
+  for (int i = 0; i < n; ++i) cdf[i] /= acc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DT_CUDA(cudaMemcpyAsync((void*)(pl->d.cdf + (size_t)slot * DT_MAX_MAP_CELLS), cdf.data(), (size_t)n * sizeof(double),
+                          cudaMemcpyHostToDevice, st));
+  DT_CUDA(cudaMemcpyAsync((void*)(pl->d.cdf_n + slot), &n, sizeof(int), cudaMemcpyHostToDevice, st));
+  DT_CUDA(cudaStreamSynchronize(st));
+  return DT_OK;
+}
+
+// test hook: the conditioning goals (P, 2) and parents (P) of all edge slots as of the last enqueued pass
+extern "C" int dt_plan_peek_slots(dt_plan* pl, float* goals_out, int32_t* parents_out, void* stream) {
+  if (!pl) return DT_E_ARG;
+  dt_ctx* ctx = pl->ctx;
+  const size_t P = (size_t)pl->d.U * pl->d.S;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (goals_out) DT_CUDA(cudaMemcpyAsync(goals_out, pl->d.slot_goal, P * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (parents_out) DT_CUDA(cudaMemcpyAsync(parents_out, pl->d.slot_parent, P * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DT_CUDA(cudaStreamSynchronize(st));
   return DT_OK;
 }
 

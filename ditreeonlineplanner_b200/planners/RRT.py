@@ -195,14 +195,14 @@ class RRT_Planner(BasePlanner):
 
     def _plan_device(self):
         """batch_mode = "device": the whole loop on the device (planners/device_planner.py, csrc/planner.cu) for this
-        one tree: 256 edge slots, no host work per pass.  run_type 0 with the uniform state sampler only."""
+        one tree: 256 edge slots, no host work per pass (any run_type, as long as no previous main path is being followed)."""
         from .device_planner import DevicePlanner
-        if self.run_type != 0 or self.init_main_path is not None:
-            raise NotImplementedError("batch_mode='device' implements run_type 0; use 'continuous' for the other run types")
+        if self.init_main_path is not None:
+            raise NotImplementedError("batch_mode='device' does not replan along a previous main path; use 'continuous'")
         start_time = time.time()
         cap = self.iteration_cap if self.iteration_cap is not None else 1 << 20
         cap = max(256, (int(cap) // 256) * 256)
-        key = (cap, int(self.action_horizon), tuple(self.prop_duration_schedule))
+        key = (cap, int(self.action_horizon), tuple(self.prop_duration_schedule), int(self.run_type))
         dp = getattr(self.sampler, "_device_planner", None)
         if dp is None or dp[0] != key or dp[1]._pushed >= dp[1].max_units:
             if dp is not None:
@@ -210,11 +210,18 @@ class RRT_Planner(BasePlanner):
             dp = (key, DevicePlanner(self.sampler, unit_slots=1, iteration_cap=cap, action_horizon=self.action_horizon,
                                      prop_duration=self.prop_duration_schedule, goal_sample_rate=self.goal_sample_rate,
                                      goal_conditioning_bias=self.goal_conditioning_bias,
-                                     local_map_scale=self.local_map_scale, max_units=64))
+                                     local_map_scale=self.local_map_scale, max_units=64, run_type=self.run_type))
             self.sampler._device_planner = dp
         unit = dict(start=np.asarray(self.start_node.state, dtype=np.float32), goal=np.asarray(self.env.goal, dtype=np.float32),
                     maze=np.float32(self.maze), maze_name=("maze", self.maze.shape, np.float32(self.maze).tobytes()),
                     seed=int(np.random.randint(0, 2 ** 31 - 1)))
+        orig_prob_map = self.env.prob_map.copy() if self.run_type >= 2 else None
+        if self.run_type >= 3:
+            self.env.update_prob_map_by_loc()              # RRT.py:126-127
+        if self.run_type >= 2:
+            unit["prob_map"] = np.array(self.env.prob_map, dtype=np.float64)
+            unit["prob_key"] = ("pm", unit["prob_map"].tobytes())
+            self.env.prob_map = orig_prob_map
         rec = dp[1].run(iter([unit]), time_budget=self.time_budget)[0]
         self.results["iterations"] = rec["results"]["iterations"]
         self.results["number_of_nodes"] = rec["results"]["number_of_nodes"]

@@ -34,7 +34,7 @@ class _Plan:
 class DevicePlanner:
     def __init__(self, sampler, unit_slots=8, iteration_cap=4096, action_horizon=8, prop_duration=(64,),
                  goal_sample_rate=0.15, goal_conditioning_bias=0.85, local_map_scale=0.2, max_units=256, max_path=4096,
-                 streams=1):
+                 streams=1, run_type=0):
         """`sampler`: the DiffusionSampler mirror that owns the packed denoiser (its max_batch should be >=
         unit_slots * 256 / streams); the remaining arguments are RRT_Planner's (planners/RRT.py:19-31).
         streams = 2 splits the unit slots over two plans on two CUDA streams and two device contexts (same packed
@@ -48,7 +48,9 @@ class DevicePlanner:
         self.max_units = int(max_units)
         self.max_path = int(max_path)
         streams = max(1, min(int(streams), self.U))
+        self.run_type = int(run_type)
         cfg = L.PlanCfg()
+        cfg.run_type = self.run_type
         cfg.edge_slots = EDGE_SLOTS
         cfg.node_cap = self.iteration_cap + 1           # every node costs at least one chunk expansion
         cfg.action_horizon = int(action_horizon)
@@ -75,6 +77,7 @@ class DevicePlanner:
             pl.h = h
             pl.pushed = pl.done = pl.passes = 0
             pl.maps = {}
+            pl.cdfs = {}
             pl.order = []
             self.plans.append(pl)
         self.h = self.plans[0].h
@@ -105,6 +108,18 @@ class DevicePlanner:
             hit = pl.maps[name] = (slot, g.shape[0], g.shape[1])
         return hit
 
+    def _cdf_slot(self, pl, key, prob_map):
+        """Slot of a unit's probability map (CarEnv.prob_map) in plan pl, staged on first use (dt_plan_set_cdf)."""
+        hit = pl.cdfs.get(key)
+        if hit is None:
+            if len(pl.cdfs) >= 64:
+                raise RuntimeError("DevicePlanner: more than 64 distinct probability maps")
+            hit = pl.cdfs[key] = len(pl.cdfs)
+            pm = np.ascontiguousarray(np.asarray(prob_map, dtype=np.float64).ravel())
+            with self._stream_of(pl):
+                pl.ctx._check(self.lib.dt_plan_set_cdf(pl.h, hit, pm.ctypes.data_as(C.c_void_p), pm.size, pl.ctx._stream()))
+        return hit
+
     def _stream_of(self, pl):
         return torch.cuda.stream(pl.stream) if pl.stream is not None else _NullCtx()
 
@@ -121,6 +136,11 @@ class DevicePlanner:
             arr[i].map_slot = slot
             arr[i].seed = int(u["seed"]) & 0xFFFFFFFF
             arr[i].unit_id = pl.pushed + i
+            arr[i].cdf_slot = -1
+            if self.run_type >= 2:
+                if u.get("prob_map") is None:
+                    raise ValueError("run_type >= 2 needs the unit's prob_map (CarEnv(run_type).prob_map)")
+                arr[i].cdf_slot = self._cdf_slot(pl, u.get("prob_key", (u["maze_name"],)), u["prob_map"])
         with self._stream_of(pl):
             pl.ctx._check(self.lib.dt_plan_push(pl.h, arr, len(units), pl.ctx._stream()))
         pl.pushed += len(units)

@@ -73,7 +73,7 @@ def run_car_unit(row, scenario_idx, run_idx, sampler, time_budget, planner_kwarg
     from .car_env import CarEnv
     from .planners.RRT import RRT_Planner
     maze = load_maze(row["maze_name"])
-    env = CarEnv(maze_map=maze, collision_checking=False)
+    env = CarEnv(maze_map=maze, collision_checking=False, run_type=int((planner_kwargs or {}).get("run_type", 0)))
     start, goal = scenario_states(row, env)
     kw = dict(env_id="carmaze", environment=env, sampler=sampler, prediction_type="actions", action_horizon=8,
               local_map_size=20, local_map_scale=0.2, global_map_scale=1.0, goal_conditioning_bias=0.85,
@@ -132,21 +132,32 @@ def gather_rows(local_units, local_rows, n_units_total, device, world, per_rank=
 _DESC_CACHE = {}
 
 
-def car_unit_descriptor(row, scenario_idx, run_idx):
+def car_unit_descriptor(row, scenario_idx, run_idx, run_type=0):
     """What the device-resident planner needs to know about one (scenario, run): start / goal exactly as
-    run_car_unit derives them (run_scenarios.py:239-246), the maze and the unit's seed.  The scenario part (an env
-    built once per row to convert its cells) is cached: the runs of a row differ in their seed only."""
-    key = (row["maze_name"], row["start_row"], row["start_col"], row["start_deg"], row["goal_row"], row["goal_col"])
+    run_car_unit derives them (run_scenarios.py:239-246), the maze, the unit's seed and -- for run_type >= 2 -- the
+    probability map the planner samples cells from (CarEnv.prob_map as of the start of plan(): the EDT prior for
+    run_type 2, its blend with the start -> goal Gaussian for run_type >= 3, car_env.py:98-137, RRT.py:126-127).
+    The scenario part (an env built once per row) is cached: the runs of a row differ in their seed only."""
+    key = (row["maze_name"], row["start_row"], row["start_col"], row["start_deg"], row["goal_row"], row["goal_col"],
+           int(run_type))
     hit = _DESC_CACHE.get(key)
     if hit is None:
         from .car_env import CarEnv
         maze = load_maze(row["maze_name"])
-        env = CarEnv(maze_map=maze, collision_checking=False)
+        env = CarEnv(maze_map=maze, collision_checking=False, run_type=int(run_type))
         start, goal = scenario_states(row, env)
         # reset() snaps the goal to its cell centre (base_planner.py:86-90 -> car_env reset)
-        hit = _DESC_CACHE[key] = dict(start=np.asarray(start, dtype=np.float32), goal=np.asarray(
-            env.cell_rowcol_to_xy(env.cell_xy_to_rowcol(goal[:2])), dtype=np.float32), maze=np.float32(maze),
-            maze_name=row["maze_name"])
+        goal_xy = env.cell_rowcol_to_xy(env.cell_xy_to_rowcol(goal[:2]))
+        hit = dict(start=np.asarray(start, dtype=np.float32), goal=np.asarray(goal_xy, dtype=np.float32),
+                   maze=np.float32(maze), maze_name=row["maze_name"])
+        if run_type >= 2:
+            env.reset(options={"reset_cell": env.cell_xy_to_rowcol(start[:2]), "reset_deg": np.rad2deg(start[2]),
+                               "goal_cell": env.cell_xy_to_rowcol(goal[:2])})
+            if run_type >= 3:
+                env.update_prob_map_by_loc()
+            hit["prob_map"] = np.array(env.prob_map, dtype=np.float64)
+            hit["prob_key"] = key
+        _DESC_CACHE[key] = hit
     return dict(hit, seed=unit_seed(scenario_idx, run_idx), key=(scenario_idx, run_idx))
 
 
@@ -157,13 +168,14 @@ def run_suite_device(sampler, units_iter, rows, planner_kwargs=None, max_units=4
     kw = dict(unit_slots=16, streams=2, iteration_cap=4096, max_units=int(max_units))
     kw.update(planner_kwargs or {})
     kw.pop("batch_size", None)
+    run_type = int(kw.get("run_type", 0))
     planner = DevicePlanner(sampler, **kw)
     mine = []
 
     def source():
         for s, r in units_iter:
             mine.append((s, r))
-            yield car_unit_descriptor(rows[s], s, r)
+            yield car_unit_descriptor(rows[s], s, r, run_type)
     try:
         recs = planner.run(source())
     finally:

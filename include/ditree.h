@@ -269,6 +269,10 @@ typedef struct {
   float goal_conditioning_bias; /* 0.85 */
   double local_map_scale;    /* 0.2 */
   double norm[16];           /* obs mean[6], obs std[6], action mean[2], action std[2] (metadata/carmaze.pt) */
+  int32_t run_type;          /* 0: uniform sampler, goal-conditioning coin (the reference's runs); 1-3: the sample is the
+                              * conditioning goal, obstacle-ahead probe per node + its penalty in the final selection
+                              * (RRT.py:154-157,201-205,233-237); >= 2: cells drawn from the unit's probability map */
+  int32_t reserved;
 } dt_plan_cfg;
 
 typedef struct {
@@ -278,7 +282,7 @@ typedef struct {
   int32_t map_slot;          /* dt_set_map_slot slot holding this unit's maze */
   uint32_t seed;
   int32_t unit_id;           /* 0..max_units-1, unique */
-  int32_t reserved;
+  int32_t cdf_slot;          /* run_type >= 2: dt_plan_set_cdf slot of env.prob_map for this unit; else -1 */
 } dt_plan_unit;
 
 typedef struct {
@@ -298,6 +302,10 @@ int dt_plan_create(dt_ctx* ctx, const dt_plan_cfg* cfg, dt_plan** out);   /* nee
 void dt_plan_destroy(dt_plan* plan);
 /* Append n units (HOST array) to the device queue; idle unit slots start on them at once.  Synchronous. */
 int dt_plan_push(dt_plan* plan, const dt_plan_unit* units_host, int n, void* stream);
+/* Stage a probability map (HOST, n = rows * cols float64, row-major: CarEnv.prob_map, car_env.py:98-137) in slot
+ * 0..63 as its normalised cumulative sum, what np.random.choice(size, p = prob_map.ravel()) searches
+ * (base_planner.py:157-160).  Synchronous. */
+int dt_plan_set_cdf(dt_plan* plan, int slot, const double* prob_host, int n, void* stream);
 /* Enqueue one pass over all unit_slots x edge_slots edges (no synchronisation) and a snapshot of the counters. */
 int dt_plan_pass(dt_plan* plan, void* stream);
 /* Counters as of the end of pass `pass_index` (0-based, one of the last four enqueued): out5 = {units popped, units
@@ -310,6 +318,9 @@ int dt_plan_fetch(dt_plan* plan, int unit_id, dt_plan_result* hdr_out, float* pa
 /* Test hook: node count, unit id, positions (xy_out: x[cap] then y[cap]) and parents of the tree in unit slot u. */
 int dt_plan_peek_tree(dt_plan* plan, int u, int32_t* n_nodes_out, int32_t* unit_id_out, float* xy_out,
                       int32_t* parent_out, int cap, void* stream);
+
+/* Test hook: conditioning goals (unit_slots * edge_slots, 2) and parent node indices of all edge slots. */
+int dt_plan_peek_slots(dt_plan* plan, float* goals_out, int32_t* parents_out, void* stream);
 
 /* Test hook for the tcgen05 GEMM core: C[M,N] (f32) = A[M,K] (bf16, row-major) * W[N,K]^T (bf16). */
 int dt_gemm_bf16(dt_ctx* ctx, const void* A, const void* W, int64_t M, int N, int K, float* C, void* stream);

@@ -92,7 +92,7 @@ class _FakeCtx:
 
 def _planner(lib, U, streams):
     pl = dp.DevicePlanner.__new__(dp.DevicePlanner)
-    pl.lib, pl.U, pl.max_units, pl.max_path, pl.stats, pl._pushed = lib, U, 1000, 16, {}, 0
+    pl.lib, pl.U, pl.max_units, pl.max_path, pl.stats, pl._pushed, pl.run_type = lib, U, 1000, 16, {}, 0, 0
     pl.plans = []
     for i in range(streams):
         p = dp._Plan()
@@ -100,7 +100,7 @@ def _planner(lib, U, streams):
         p.ctx, p.stream = _FakeCtx(), None
         p.h = C.c_void_p(lib.new_plan(p.U))
         p.pushed = p.done = p.passes = 0
-        p.maps, p.order = {}, []
+        p.maps, p.cdfs, p.order = {}, {}, []
         pl.plans.append(p)
     return pl
 

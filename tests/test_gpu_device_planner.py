@@ -196,3 +196,75 @@ def test_goal_reached_in_flight(sampler, mazes):
     # the state before the last one was still outside the disc (the edge stops AT the goal step)
     assert np.linalg.norm(r["path"][-3, :2].astype(np.float64) - g) >= 0.5 or len(r["actions"]) == 1
     assert recs[1]["finished"] and not recs[1]["goal_reached"] and recs[1]["results"]["iterations"] == 768
+
+
+def test_probability_map_sampler_on_device(sampler, mazes):
+    """run_type 2: the state sampler draws cells from the unit's probability map on the device
+    (base_planner.py:157-160,176-183) and the sample itself is the conditioning goal (RRT.py:157).  One pass of eight
+    copies of a scenario with different seeds = 2048 fresh samples, read back through the test hook: every exploring
+    sample is the centre of a cell with non-zero probability, the goal is drawn at its 15 % rate, and the empirical
+    distribution over 4 x 4-cell blocks matches the map."""
+    import ctypes as C
+    from ditreeonlineplanner_b200 import load_scenarios
+    from ditreeonlineplanner_b200.planners.device_planner import DevicePlanner
+    from ditreeonlineplanner_b200.scenarios import car_unit_descriptor
+    rows = load_scenarios("test_scenarios_car")
+    s_idx = next(i for i, r in enumerate(rows) if r["maze_name"] == "boxes")
+    units = []
+    for k in range(8):
+        d = car_unit_descriptor(rows[s_idx], s_idx, k, run_type=2)
+        units.append(d)
+    pm = units[0]["prob_map"]
+    R, Cc = pm.shape
+    assert abs(pm.sum() - 1.0) < 1e-9 and (pm[mazes["boxes"] == 1] == 0).all()
+    pl = DevicePlanner(sampler, unit_slots=8, iteration_cap=4096, max_units=16, run_type=2)
+    pl._push(units)
+    p0 = pl.plans[0]
+    p0.ctx._check(pl.lib.dt_plan_pass(p0.h, p0.ctx._stream()))
+    goals = np.zeros((8 * 256, 2), np.float32)
+    p0.ctx._check(pl.lib.dt_plan_peek_slots(p0.h, goals.ctypes.data_as(C.c_void_p), None, p0.ctx._stream()))
+    pl.close()
+    gx, gy = units[0]["goal"]
+    is_goal = (np.abs(goals[:, 0] - gx) < 1e-6) & (np.abs(goals[:, 1] - gy) < 1e-6)
+    col = goals[:, 0] + Cc / 2 - 0.5
+    row = R / 2 - goals[:, 1] - 0.5
+    assert np.allclose(col, np.round(col), atol=1e-5) and np.allclose(row, np.round(row), atol=1e-5)   # cell centres
+    ri, ci = np.round(row).astype(int), np.round(col).astype(int)
+    assert (pm[ri[~is_goal], ci[~is_goal]] > 0).all()
+    # goal bias: 15 % plus the explorers that happened to draw the goal's own cell
+    expect_goal = 0.15 + 0.85 * pm[int(round(R / 2 - gy - 0.5)), int(round(gx + Cc / 2 - 0.5))]
+    assert abs(is_goal.mean() - expect_goal) < 0.04, (is_goal.mean(), expect_goal)
+    emp = np.zeros_like(pm)
+    np.add.at(emp, (ri[~is_goal], ci[~is_goal]), 1.0)
+    emp /= emp.sum()
+    blk = lambda a: a.reshape(R // 4, 4, Cc // 4, 4).sum((1, 3))
+    tv = 0.5 * np.abs(blk(emp) - blk(pm)).sum()
+    assert tv < 0.1, tv
+
+
+def test_run_type_2_matches_host_planner(sampler):
+    """The device loop with the probability-map sampler, the sample as conditioning goal and the obstacle-ahead
+    penalty against the host-driven batched planner with the same run_type, at equal passes per edge slot."""
+    from ditreeonlineplanner_b200 import load_scenarios
+    from ditreeonlineplanner_b200 import scenarios as sc
+    from ditreeonlineplanner_b200.planners.device_planner import DevicePlanner
+    rows = load_scenarios("test_scenarios_car")
+    idx, runs, passes = [0, 4, 8], 2, 8
+    units = [sc.car_unit_descriptor(rows[s], s, r, run_type=2) for s in idx for r in range(runs)]
+    pl = DevicePlanner(sampler, unit_slots=3, iteration_cap=256 * passes, max_units=32, run_type=2)
+    recs = pl.run(iter(units))
+    pl.close()
+    assert all(r["finished"] and r["error"] == 0 for r in recs)
+    for r, u in zip(recs, units):
+        if r["path"] is not None:
+            _replay(r, u)
+    dev_nodes = np.mean([r["results"]["number_of_nodes"] / max(1, r["results"]["iterations"]) for r in recs])
+    host = []
+    for s in idx:
+        for r in range(runs):
+            row = sc.run_car_unit(rows[s], s, r, sampler, 1e9, {"batch_size": 256, "iteration_cap": 512 * passes, "run_type": 2})
+            host.append(max(row[6], 1) / max(1, row[7]))
+    host_nodes = float(np.mean(host))
+    msg = f"run_type 2, nodes per chunk expansion: device {dev_nodes:.4f}, host batched {host_nodes:.4f}"
+    print(msg)
+    assert abs(dev_nodes - host_nodes) <= 0.25 * max(dev_nodes, host_nodes), msg

@@ -50,6 +50,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+        // (a suspend-time hint -- the warp may sleep instead of spinning -- was measured: 20.50 k vs 20.56 k edges/s
+        // without it, same box, two runs each; not used)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)

@@ -56,6 +56,10 @@ struct dt_ctx {
   size_t wide_bytes = 0;
   void* d_splitk = nullptr;   // fixed-size fp32 scratch of the split-K path (gemm.cu)
   bool splitk_on = true;      // dt_set_option(ctx, "splitk", 0) restores batch-size independent bits
+  // programmatic dependent launch for the denoiser's kernel chain (dt_set_option(ctx, "pdl", 0) or DITREE_PDL=0
+  // turn it off): a kernel's CTAs are scheduled, and run their prologue (barrier init, TMEM allocation, tensor-map
+  // prefetch), while the previous kernel's last CTAs drain; griddepcontrol.wait orders all memory traffic
+  bool pdl_on = true;
   int64_t launches = 0;
   int sm_count = 148;
   dt_denoiser* den = nullptr;
@@ -91,6 +95,26 @@ static inline int dt_fail_cuda(dt_ctx* ctx, cudaError_t e, const char* where) {
     ctx->launches++;                                                       \
   } while (0)
 
+// Launch with (or without) the programmatic-stream-serialization attribute.  ONLY for kernels that execute
+// dt_pdl_wait() before their first global-memory access: a kernel launched with the attribute that never waits
+// would race with its predecessor.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dt_launch(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int dt_ensure_scratch(dt_ctx* ctx, size_t bytes);
 dt_model_cfg dt_denoiser_cfg(dt_ctx* ctx);  // denoiser.cu: configuration of the loaded denoiser (ctx->den != nullptr)
 
@@ -117,6 +141,12 @@ static inline MapView dt_map_view(const dt_ctx* ctx) {
 __device__ __forceinline__ uint32_t dt_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// Programmatic dependent launch (sm_90+).  dt_pdl_launch: the next kernel in the stream may be scheduled from now on
+// (its CTAs take whatever SM resources are free and block in dt_pdl_wait).  dt_pdl_wait: returns when every kernel
+// this one depends on has COMPLETED and its writes are visible; a no-op for a kernel launched without the attribute.
+__device__ __forceinline__ void dt_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void dt_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Stage the occupancy grid into shared memory with one 1-D bulk TMA copy (cp.async.bulk,
 // SASS UBLKCP) completing on an mbarrier.  Call from every thread of the block; `bar` is a

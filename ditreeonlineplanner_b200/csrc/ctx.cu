@@ -18,6 +18,10 @@ extern "C" int dt_ctx_create(int device, dt_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DT_E_CUDA; }
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    const char* e = getenv("DITREE_PDL");
+    if (e && e[0] == '0') ctx->pdl_on = false;
+  }
   if (prop.major != 10) {
     // sm_100a cubins only load on compute capability 10.x parts; fail loudly instead of later
     fprintf(stderr, "libditree: device %d is sm_%d%d, this library is built for sm_100a only\n", device, prop.major,
@@ -63,6 +67,15 @@ extern "C" int dt_set_option(dt_ctx* ctx, const char* name, int value) {
       dt_denoiser_drop_graphs(ctx);
     }
     ctx->splitk_on = value != 0;
+    return DT_OK;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    if (ctx->pdl_on != (value != 0)) {  // captured graphs hold the launch attributes of their kernel nodes
+      DT_CUDA(cudaSetDevice(ctx->device));
+      DT_CUDA(cudaDeviceSynchronize());
+      dt_denoiser_drop_graphs(ctx);
+    }
+    ctx->pdl_on = value != 0;
     return DT_OK;
   }
   return dt_fail(ctx, DT_E_ARG, "dt_set_option: unknown option");

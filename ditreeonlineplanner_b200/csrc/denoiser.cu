@@ -92,6 +92,7 @@ struct dt_denoiser {
   float norm_host[16];
   bool norm_valid = false;
   float* mish_t = nullptr;     // [DEN_KMAX][256]
+  float* time_h = nullptr;     // [DEN_KMAX][1024] hidden layer of the time MLP
   __nv_bfloat16* cond_in = nullptr;  // [MB][kc_pad]
   __nv_bfloat16* col = nullptr;      // im2col buffer
   __nv_bfloat16* e[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -110,6 +111,8 @@ __device__ __forceinline__ float mishf(float x) {
 
 // fp32 sample (B,T,A) -> bf16 (B,T,64), channels >= A zero
 __global__ void k_prep_sample(const float* __restrict__ a, int64_t rows, int A, __nv_bfloat16* __restrict__ x) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t n = rows * 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i & 63);
@@ -124,6 +127,8 @@ __global__ void __launch_bounds__(256)
 k_final_euler(const __nv_bfloat16* __restrict__ f, int64_t rows, int C0, int A, const float* __restrict__ w,
               const float* __restrict__ bias, float dt, float* __restrict__ a, float* __restrict__ vel_out,
               const float* __restrict__ norm /* mean[A], std[A] or null */) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * wpb) {
@@ -167,6 +172,8 @@ __global__ void __launch_bounds__(256)
 k_final_euler_a2(const __nv_bfloat16* __restrict__ f, int64_t rows, const float* __restrict__ w,
                  const float* __restrict__ bias, float dt, float* __restrict__ a, float* __restrict__ vel_out,
                  const float* __restrict__ norm) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   constexpr int C0 = 64 * NI;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -214,6 +221,8 @@ static int launch_final_euler(dt_ctx* ctx, const __nv_bfloat16* f, int64_t rows,
 // Mish([emb | cond]) as the bf16 A operand of the per-candidate FiLM GEMM, zero padded to kc_pad
 __global__ void k_film_input(const float* __restrict__ emb, int emb_ld, int E, const float* __restrict__ cond, int G,
                              int64_t B, int kc_pad, __nv_bfloat16* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t n = B * kc_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % kc_pad);
@@ -231,38 +240,53 @@ struct TimeSteps {
   float t[DEN_KMAX];  // passed by value: no host staging buffer whose lifetime a launch would have to outlive
 };
 
+// Two launches, one warp per output neuron (coalesced reads of its weight row, shuffle reduction): the 2 MB of fp32
+// weights are pulled by 128 / 32 blocks per step instead of one (one block per step took 275 us -- a fifth of a
+// graph-replayed small-batch sampler call, which recomputes the table every time).
 __global__ void __launch_bounds__(256)
-k_time_mlp(TimeSteps ts, const float* __restrict__ w1, const float* __restrict__ b1,
-           const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out) {
-  __shared__ float s_e[256];
-  __shared__ float s_h[1024];
-  const int k = blockIdx.x, tid = threadIdx.x;
+k_time_mlp1(TimeSteps ts, const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ hid) {
+  dt_pdl_launch();
+  dt_pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x >> 7;                                     // 128 blocks of 8 neurons per step
+  const int o = ((blockIdx.x & 127) << 3) + (threadIdx.x >> 5);      // hidden neuron 0..1023
   const float t = ts.t[k];
-  {
-    const int i = tid & 127;
-    const float f = expf((float)i * -(logf(10000.0f) / 127.0f));
-    const float arg = t * f;
-    s_e[tid] = tid < 128 ? sinf(arg) : cosf(arg);
+  const float* wr = w1 + o * 256;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j * 32 + lane;                                     // sinusoid: sin on 0..127, cos on 128..255
+    const float arg = t * expf((float)(c & 127) * -(logf(10000.0f) / 127.0f));
+    acc += wr[c] * (c < 128 ? sinf(arg) : cosf(arg));
   }
-  __syncthreads();
-  for (int o = tid; o < 1024; o += 256) {
-    float acc = b1[o];
-    const float* wr = w1 + o * 256;
-    for (int j = 0; j < 256; ++j) acc += wr[j] * s_e[j];
-    s_h[o] = mishf(acc);
-  }
-  __syncthreads();
-  {
-    float acc = b2[tid];
-    const float* wr = w2 + tid * 1024;
-    for (int j = 0; j < 1024; ++j) acc += wr[j] * s_h[j];
-    out[k * 256 + tid] = mishf(acc);
-  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) hid[k * 1024 + o] = mishf(acc + b1[o]);
+}
+
+__global__ void __launch_bounds__(256)
+k_time_mlp2(const float* __restrict__ hid, const float* __restrict__ w2, const float* __restrict__ b2,
+            float* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x >> 5;                                     // 32 blocks of 8 outputs per step
+  const int o = ((blockIdx.x & 31) << 3) + (threadIdx.x >> 5);       // output 0..255
+  const float* wr = w2 + o * 1024;
+  const float* h = hid + k * 1024;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) acc += wr[j * 32 + lane] * h[j * 32 + lane];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) out[k * 256 + o] = mishf(acc + b2[o]);
 }
 
 // per-step FiLM part: film_time[k][n] = sum_j Wt[n][j] * mish_t[k][j]; one warp per n
 __global__ void __launch_bounds__(256)
 k_film_time(const float* __restrict__ wt, const float* __restrict__ mish_t, int F, int K, float* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= F) return;
@@ -283,6 +307,8 @@ k_film_time(const float* __restrict__ wt, const float* __restrict__ mish_t, int 
 // im2col: rows (b, oy, ox), K order (ky, kx, c), zero padded to kpad
 __global__ void k_im2col(const __nv_bfloat16* __restrict__ in, int64_t B, int H, int W, int C, int k, int stride,
                          int pad, int OH, int OW, int kpad, __nv_bfloat16* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t n = B * OH * OW * (int64_t)kpad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int kk = (int)(i % kpad);
@@ -306,6 +332,8 @@ __global__ void k_im2col(const __nv_bfloat16* __restrict__ in, int64_t B, int H,
 // vectorised im2col for C % 8 == 0 (every encoder conv except conv1): one 16-byte copy per thread
 __global__ void k_im2col_v8(const __nv_bfloat16* __restrict__ in, int64_t B, int H, int W, int C, int k, int stride,
                             int pad, int OH, int OW, __nv_bfloat16* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int c8n = C / 8;
   const int64_t n = B * OH * OW * (int64_t)(k * k) * c8n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -366,6 +394,8 @@ k_gn2d(const __nv_bfloat16* __restrict__ x, int64_t B, int HW, int C, const floa
 
 __global__ void k_maxpool3s2(const __nv_bfloat16* __restrict__ in, int64_t B, int H, int W, int C, int OH, int OW,
                              __nv_bfloat16* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t n = B * OH * OW * (int64_t)C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -386,6 +416,8 @@ __global__ void k_maxpool3s2(const __nv_bfloat16* __restrict__ in, int64_t B, in
 
 __global__ void k_avgpool(const __nv_bfloat16* __restrict__ in, int64_t B, int HW, int C,
                           __nv_bfloat16* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t n = B * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -398,6 +430,8 @@ __global__ void k_avgpool(const __nv_bfloat16* __restrict__ in, int64_t B, int H
 
 // local map (B,N,N) bf16 -> itself viewed as (B, N, N, 1); conv1's im2col reads it directly (C = 1)
 __global__ void k_copy_cols(const float* __restrict__ in, int ld_in, int64_t B, int n, float* __restrict__ out) {
+  dt_pdl_launch();
+  dt_pdl_wait();
   const int64_t tot = B * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = in[(i / n) * ld_in + (i % n)];
@@ -743,6 +777,7 @@ extern "C" int dt_load_denoiser(dt_ctx* ctx, const dt_tensor_desc* tensors, int 
   d->film_cand = arena<float>(d, MB * d->F, &aok);
   d->film_time = arena<float>(d, (size_t)DEN_KMAX * d->F, &aok);
   d->mish_t = arena<float>(d, (size_t)DEN_KMAX * 256, &aok);
+  d->time_h = arena<float>(d, (size_t)DEN_KMAX * 1024, &aok);
   d->norm_dev = arena<float>(d, 16, &aok);
   d->g_noise = arena<float>(d, (size_t)DEN_GRAPH_MAXB * T * A, &aok);
   d->g_out = arena<float>(d, (size_t)DEN_GRAPH_MAXB * T * A, &aok);
@@ -796,10 +831,11 @@ static int launch_final_euler(dt_ctx* ctx, const __nv_bfloat16* f, int64_t rows,
                               const float* bias, float dt, float* a, float* vel_out, const float* norm,
                               cudaStream_t st) {
   const int grid = ew_grid(rows * 32, ctx);
-  if (A == 2 && C0 == 512) k_final_euler_a2<8><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
-  else if (A == 2 && C0 == 256) k_final_euler_a2<4><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
-  else if (A == 2 && C0 == 64) k_final_euler_a2<1><<<grid, 256, 0, st>>>(f, rows, w, bias, dt, a, vel_out, norm);
-  else k_final_euler<<<grid, 256, 0, st>>>(f, rows, C0, A, w, bias, dt, a, vel_out, norm);
+  const bool pdl = ctx->pdl_on;
+  if (A == 2 && C0 == 512) dt_launch(pdl, k_final_euler_a2<8>, grid, 256, 0, st, f, rows, w, bias, dt, a, vel_out, norm);
+  else if (A == 2 && C0 == 256) dt_launch(pdl, k_final_euler_a2<4>, grid, 256, 0, st, f, rows, w, bias, dt, a, vel_out, norm);
+  else if (A == 2 && C0 == 64) dt_launch(pdl, k_final_euler_a2<1>, grid, 256, 0, st, f, rows, w, bias, dt, a, vel_out, norm);
+  else dt_launch(pdl, k_final_euler, grid, 256, 0, st, f, rows, C0, A, w, bias, dt, a, vel_out, norm);
   DT_LAUNCH_CHECK("k_final_euler");
   return DT_OK;
 }
@@ -1041,10 +1077,10 @@ static int enc_conv_gn(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_b
   }
   if (!direct) {
     if (Cin % 8 == 0 && w.Ktot == k * k * Cin) {
-      k_im2col_v8<<<ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
+      dt_launch(ctx->pdl_on, k_im2col_v8, ew_grid(rows * (w.Ktot / 8), ctx), 256, 0, st, in, B, H, W, Cin, k, stride, pad, OH, OW, d->col);
       DT_LAUNCH_CHECK("k_im2col_v8");
     } else {
-      k_im2col<<<ew_grid(rows * w.Ktot, ctx), 256, 0, st>>>(in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
+      dt_launch(ctx->pdl_on, k_im2col, ew_grid(rows * w.Ktot, ctx), 256, 0, st, in, B, H, W, Cin, k, stride, pad, OH, OW, w.Ktot, d->col);
       DT_LAUNCH_CHECK("k_im2col");
     }
     g.nseg = 1;
@@ -1070,7 +1106,7 @@ static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm,
   int H = (NM + 6 - 7) / 2 + 1;  // conv1 7x7 s2 p3, then GroupNorm + ReLU
   if ((rc = enc_conv_gn(ctx, d, d->enc_conv1, lm, B, NM, NM, 1, 7, 2, 3, H, H, nullptr, 1, d->e[1], st))) return rc;
   const int PH = (H + 2 - 3) / 2 + 1;  // maxpool 3x3 s2 p1
-  k_maxpool3s2<<<ew_grid(B * PH * PH * 64, ctx), 256, 0, st>>>(d->e[1], B, H, H, 64, PH, PH, d->e[0]);
+  dt_launch(ctx->pdl_on, k_maxpool3s2, ew_grid(B * PH * PH * 64, ctx), 256, 0, st, d->e[1], B, H, H, 64, PH, PH, d->e[0]);
   DT_LAUNCH_CHECK("k_maxpool3s2");
   __nv_bfloat16* cur = d->e[0];
   __nv_bfloat16* t1 = d->e[1];
@@ -1099,7 +1135,7 @@ static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm,
   }
   const __nv_bfloat16* feat = cur;
   if (H * H > 1) {
-    k_avgpool<<<ew_grid(B * 512, ctx), 256, 0, st>>>(cur, B, H * H, 512, t1);
+    dt_launch(ctx->pdl_on, k_avgpool, ew_grid(B * 512, ctx), 256, 0, st, cur, B, H * H, 512, t1);
     DT_LAUNCH_CHECK("k_avgpool");
     feat = t1;
   }
@@ -1122,7 +1158,7 @@ static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm,
 // per-candidate FiLM part for all 12 residual blocks: one GEMM (B x kc_pad) x (kc_pad x F)
 static int film_candidates(dt_ctx* ctx, dt_denoiser* d, const float* emb, int emb_ld, const float* cond, int64_t B,
                            cudaStream_t st) {
-  k_film_input<<<ew_grid(B * d->kc_pad, ctx), 256, 0, st>>>(emb, emb_ld, d->E, cond, d->G, B, d->kc_pad, d->cond_in);
+  dt_launch(ctx->pdl_on, k_film_input, ew_grid(B * d->kc_pad, ctx), 256, 0, st, emb, emb_ld, d->E, cond, d->G, B, d->kc_pad, d->cond_in);
   DT_LAUNCH_CHECK("k_film_input");
   ConvGemm g;
   g.a[0] = ActSrc{d->cond_in, d->kc_pad, (int)B, 1};
@@ -1150,9 +1186,11 @@ static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, 
   TimeSteps ts;
   memset(&ts, 0, sizeof(ts));
   memcpy(ts.t, ts_host, K * sizeof(float));
-  k_time_mlp<<<K, 256, 0, st>>>(ts, d->t_w1, d->t_b1, d->t_w2, d->t_b2, d->mish_t);
-  DT_LAUNCH_CHECK("k_time_mlp");
-  k_film_time<<<(d->F + 7) / 8, 256, 0, st>>>(d->film_wt, d->mish_t, d->F, K, d->film_time);
+  dt_launch(ctx->pdl_on, k_time_mlp1, K * 128, 256, 0, st, ts, d->t_w1, d->t_b1, d->time_h);
+  DT_LAUNCH_CHECK("k_time_mlp1");
+  dt_launch(ctx->pdl_on, k_time_mlp2, K * 32, 256, 0, st, d->time_h, d->t_w2, d->t_b2, d->mish_t);
+  DT_LAUNCH_CHECK("k_time_mlp2");
+  dt_launch(ctx->pdl_on, k_film_time, (d->F + 7) / 8, 256, 0, st, d->film_wt, d->mish_t, d->F, K, d->film_time);
   DT_LAUNCH_CHECK("k_film_time");
   d->film_time_K = K;
   d->film_time_stream = (void*)st;
@@ -1177,7 +1215,7 @@ extern "C" int dt_encode_map(dt_ctx* ctx, const void* local_map, int64_t B, floa
     const int64_t nb = (B - b0 < d->MB) ? (B - b0) : d->MB;
     int rc = encoder_forward(ctx, d, lm + b0 * d->NM * d->NM, nb, st);
     if (rc) return rc;
-    k_copy_cols<<<ew_grid(nb * d->E, ctx), 256, 0, st>>>(d->emb, d->emb_pad, nb, d->E, emb_out + b0 * d->E);
+    dt_launch(ctx->pdl_on, k_copy_cols, ew_grid(nb * d->E, ctx), 256, 0, st, d->emb, d->emb_pad, nb, d->E, emb_out + b0 * d->E);
     DT_LAUNCH_CHECK("k_copy_cols");
   }
   return DT_OK;
@@ -1196,7 +1234,7 @@ extern "C" int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* em
     const int64_t nb = (B - b0 < d->MB) ? (B - b0) : d->MB;
     if ((rc = film_candidates(ctx, d, emb + b0 * d->E, d->E, cond + b0 * d->G, nb, st))) return rc;
     const int64_t rows = nb * d->T;
-    k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(sample + b0 * d->T * d->A, rows, d->A, d->X);
+    dt_launch(ctx->pdl_on, k_prep_sample, ew_grid(rows * 64, ctx), 256, 0, st, sample + b0 * d->T * d->A, rows, d->A, d->X);
     DT_LAUNCH_CHECK("k_prep_sample");
     if ((rc = unet_body(ctx, d, nb, d->film_time, st))) return rc;
     if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, 0.f, nullptr,
@@ -1220,7 +1258,8 @@ static int fm_sample_body(dt_ctx* ctx, dt_denoiser* d, const float* noise, const
     if ((rc = film_candidates(ctx, d, d->emb, d->emb_pad, cond + b0 * d->G, nb, st))) return rc;
     DT_CUDA(cudaMemcpyAsync(a, noise + b0 * d->T * d->A, rows * d->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     for (int k = 0; k < K; ++k) {
-      k_prep_sample<<<ew_grid(rows * 64, ctx), 256, 0, st>>>(a, rows, d->A, d->X);
+      // (k == 0 follows the copy of the noise: a memcpy node is no programmatic-launch primary)
+      dt_launch(ctx->pdl_on && k > 0, k_prep_sample, ew_grid(rows * 64, ctx), 256, 0, st, a, rows, d->A, d->X);
       DT_LAUNCH_CHECK("k_prep_sample");
       if ((rc = unet_body(ctx, d, nb, d->film_time + (size_t)k * d->F, st))) return rc;
       if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k], a, nullptr,

@@ -372,6 +372,7 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * BN;  // 128, 256 or 512: powers of two >= 32
   DBG_T(tk0);
+  dt_pdl_launch();  // the next kernel's CTAs may take this SM's resources as soon as this CTA leaves
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P::kStages; ++s) {
@@ -404,6 +405,9 @@ k_conv_gemm(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // everything above (barriers, tensor-map prefetch, TMEM allocation, the pair's cluster sync) touched no global
+  // memory and overlapped the previous kernel's tail; from here on its output is read
+  dt_pdl_wait();
 
   // tiles are (unit-level M tile, N tile); a unit-level M tile is CG * 128 rows, CTA `rank` owns its 128-row slice
   const int unit_m_tiles = (g.num_m_tiles + CG - 1) / CG;
@@ -1096,13 +1100,15 @@ static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap&
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = P::kBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->pdl_on ? 2 : 1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->prof_on) {
     e0 = dt_prof_event(ctx);
@@ -1272,6 +1278,8 @@ k_splitk_epi(SplitKEpi p) {
   extern __shared__ __align__(16) float s_y[];  // [T / CS][gw]
   __shared__ float s_a[SPLITK_EPI_THREADS], s_b[SPLITK_EPI_THREADS];
   __shared__ float s_part[2];
+  dt_pdl_launch();
+  dt_pdl_wait();  // the partial sums are the previous kernel's output
   const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
   const int win = blockIdx.x / CS;
   const int windows = p.N / p.gw;
@@ -1429,13 +1437,15 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   cfg.blockDim = dim3(SPLITK_EPI_THREADS);
   cfg.dynamicSmemBytes = (size_t)(e.T / cs) * e.gw * sizeof(float);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->pdl_on ? 2 : 1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->prof_on) {  // the reduction is part of the layer's cost: recorded as epi = 2 (no flops of its own)
     e0 = dt_prof_event(ctx);

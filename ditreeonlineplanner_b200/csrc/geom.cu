@@ -33,6 +33,10 @@ k_collide_car(MapView m, QMapView q, const float* __restrict__ x, const float* _
 #ifndef COLL4_MINB
 #define COLL4_MINB 3  // resident blocks per SM the register allocation is held to (80 registers, no spills)
 #endif
+// LAYOUT 0: x, y, theta anywhere (element stride `stride`); 1: rows of exactly (x, y, theta) -- y = x + 1, theta = x + 2,
+// stride 3, 16-byte aligned: a thread's four states are three 128-bit loads; 2: x, y, theta adjacent in rows of any even
+// stride (the planner's (B, 6) states), 8-byte aligned: one 64-bit + one 32-bit load per state off one base address.
+template <int LAYOUT>
 __global__ void __launch_bounds__(GEOM_THREADS, COLL4_MINB)
 k_collide_car4(MapView m, QMapView q, const float* __restrict__ x, const float* __restrict__ y,
                const float* __restrict__ th, int64_t stride, int64_t B, uint8_t* __restrict__ out,
@@ -46,12 +50,30 @@ k_collide_car4(MapView m, QMapView q, const float* __restrict__ x, const float* 
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, total = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = gtid; t < quads; t += total) {
     float xs[4], ys[4], ts[4];
+    if (LAYOUT == 1) {
+      const float4* p = reinterpret_cast<const float4*>(x) + 3 * t;
+      const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+      xs[0] = a.x; ys[0] = a.y; ts[0] = a.z;
+      xs[1] = a.w; ys[1] = b.x; ts[1] = b.y;
+      xs[2] = b.z; ys[2] = b.w; ts[2] = c.x;
+      xs[3] = c.y; ys[3] = c.z; ts[3] = c.w;
+    } else if (LAYOUT == 2) {
+      const float* p = x + 4 * t * stride;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t o = (4 * t + j) * stride;
-      xs[j] = x[o];
-      ys[j] = y[o];
-      ts[j] = th[o];
+      for (int j = 0; j < 4; ++j) {
+        const float2 xy = __ldg(reinterpret_cast<const float2*>(p + j * stride));
+        xs[j] = xy.x;
+        ys[j] = xy.y;
+        ts[j] = __ldg(p + j * stride + 2);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t o = (4 * t + j) * stride;
+        xs[j] = x[o];
+        ys[j] = y[o];
+        ts[j] = th[o];
+      }
     }
     uint32_t flags = 0, rare = 0;
 #pragma unroll
@@ -514,8 +536,16 @@ extern "C" int dt_collide_car(dt_ctx* ctx, const float* x, const float* y, const
     q.bytes = 0;
   }
   if (q.g && B >= 4 && (reinterpret_cast<uintptr_t>(flags_out) & 3u) == 0) {
-    k_collide_car4<<<grid_for((B + 3) / 4, GEOM_THREADS, ctx, COLL4_MINB), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
-        m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+    const int grid = grid_for((B + 3) / 4, GEOM_THREADS, ctx, COLL4_MINB);
+    const size_t smem = m.bytes + q.bytes;
+    const bool rows = (y == x + 1) && (theta == x + 2);
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(x);
+    if (rows && stride == 3 && (xa & 15u) == 0)
+      k_collide_car4<1><<<grid, GEOM_THREADS, smem, (cudaStream_t)stream>>>(m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+    else if (rows && stride % 2 == 0 && (xa & 7u) == 0)
+      k_collide_car4<2><<<grid, GEOM_THREADS, smem, (cudaStream_t)stream>>>(m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
+    else
+      k_collide_car4<0><<<grid, GEOM_THREADS, smem, (cudaStream_t)stream>>>(m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
   } else {
     k_collide_car<<<grid_for(B, GEOM_THREADS, ctx), GEOM_THREADS, m.bytes + q.bytes, (cudaStream_t)stream>>>(
         m, q, x, y, theta, stride, B, flags_out, ctx->d_status);
@@ -678,6 +708,177 @@ k_local_map_fast(MapView m, const float* __restrict__ x, const float* __restrict
   }
 }
 
+// ---- quad variant (N % 4 == 0: the reference's 20 x 20 and 16 x 16 maps) -------------------------------------------
+// Same lattice arithmetic, laid out for fewer issue slots per point (the kernel is issue-bound, not HBM-bound):
+//   * a HALF-warp per pose (two poses per warp): 100 quads of a 20 x 20 map fill 7 x 16 lanes to 89 % (a whole warp
+//     would run 4 x 32 at 78 %), and the per-pose set-up (MUFU sin / cos, six lattice coefficients, error bound) is
+//     paid once per two poses;
+//   * a lane owns FOUR consecutive points of one row per iteration: one base coordinate pair + three increments, one
+//     128-bit (fp32) or 64-bit (bf16) store, no row-wrap cases;
+//   * a point closer to a cell border than the fp32 error bound is NOT re-decided in line (one such lane stalled its
+//     whole warp for the ~400-instruction float64 code in 1 of 20 warp iterations): the quad gets its provisional
+//     table value and goes onto a per-block list; after the block's poses are done the list is worked off by all
+//     threads in parallel, one float64 decision each, overwriting the provisional value (ordered by the barrier).
+#define LMQ_CAP 1024
+template <typename OutT, bool kMulti, int NT>
+__global__ void __launch_bounds__(GEOM_THREADS, LM_MINB)
+k_local_map_quad(MapView m, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ th,
+                 int64_t stride, int64_t B, Axis ax, OutT* __restrict__ out, MultiMap mm) {
+  constexpr int NN = NT * NT, NQ = NT / 4, Q = NT * NQ, IT = (Q + 15) / 16;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ uint64_t bar;
+  __shared__ unsigned int s_cnt;
+  __shared__ unsigned long long s_list[LMQ_CAP];   // pose * Q + quad
+  __shared__ float2 s_ij[16 * IT];
+  __shared__ uint32_t s_base;
+  const int hw_per_block = blockDim.x >> 4;        // half-warps = poses in flight per block
+  if (kMulti) {
+    const int grp = (int)((blockIdx.x * (int64_t)hw_per_block) / mm.group_size);
+    int slot = mm.slot_of_group[grp];
+    slot = (slot < 0 || slot >= DT_MAX_MAP_SLOTS) ? 0 : slot;
+    m = mm.table[slot].m;
+    if (m.g == nullptr) return;
+  }
+  uint8_t* s_map = s_raw;
+  float* s_tab = reinterpret_cast<float*>(s_raw + ((m.bytes + 15) & ~15));
+  if (threadIdx.x == 0) s_cnt = 0;
+  dt_stage_map(s_map, &bar, m);
+  const int pitch = m.cols + 2 * LM_PAD, trows = m.rows + 2 * LM_PAD;
+  for (int e = threadIdx.x; e < trows * pitch; e += blockDim.x) {
+    const int r = dt_clampi(e / pitch - LM_PAD, 0, m.rows - 1), c = dt_clampi(e % pitch - LM_PAD, 0, m.cols - 1);
+    const float v = (float)s_map[r * m.cols + c];
+    s_tab[e] = sizeof(OutT) == 4 ? v : v * 2.0f - 1.0f;   // bf16 output: the sampler's rescale (fm_policy.py:152)
+  }
+  // (row, first column) of the quad l16 + 16 k of this lane, as floats: the same for every pose -- one 64-bit shared
+  // load per quad (fourteen registers would cost the third block per SM, re-deriving them five instructions per quad)
+  if (threadIdx.x < 16 * IT) {
+    const int qd = threadIdx.x;
+    const int i = qd / NQ, j = 4 * (qd - i * NQ);
+    s_ij[qd] = make_float2((float)i, (float)j);
+  }
+  if (threadIdx.x == 0)
+    s_base = dt_smem_u32(s_tab) + 4u * (((uint32_t)LM_PAD - 0x4B400000u) * (uint32_t)(pitch + 1));  // wraps
+  __syncthreads();
+  const int l16 = threadIdx.x & 15;
+  const double cx = xmul(xdiv((double)m.cols, 2.0), m.s), cy = xmul(xdiv((double)m.rows, 2.0), m.s);
+  const float inv_s = (float)(1.0 / m.s);
+  const float cxs = (float)(cx / m.s - 0.5), cys = (float)(cy / m.s - 0.5);
+  const float st_s = ax.startf * inv_s, sp_s = ax.stepf * inv_s;
+  const float span = (float)((cx + cy) / m.s) + 2.0f * ax.amax * inv_s;
+  const float MAGIC = 12582912.0f;                       // 1.5 * 2^23: (v + MAGIC) - MAGIC = rint(v)
+  // one base register: address = (bits(tu) * pitch + bits(tw)) * 4 + base (wrapping).  Read back from shared memory so
+  // that ptxas cannot take the constant apart again (it re-split it into an extra add per point)
+  const uint32_t tab_u = *reinterpret_cast<volatile uint32_t*>(&s_base);
+  const uint32_t upitch = (uint32_t)pitch;
+  const bool reach_ok = 1.4143f * ax.amax * inv_s + 1.6f < (float)LM_PAD;
+  auto exact_value = [&](float thf, float pxf, float pyf, int i, int j) -> float {
+    const float v = (float)s_map[lm_exact_cell(m.rows, m.cols, m.s, thf, pxf, pyf, ax.v[j], ax.v[i])];
+    return sizeof(OutT) == 4 ? v : v * 2.0f - 1.0f;
+  };
+  auto store4 = [&](OutT* o, int qd, const float (&v)[4]) {
+    if (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(o + 4 * qd) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(o + 4 * qd) = pk;
+    }
+  };
+  for (int64_t b = blockIdx.x * (int64_t)hw_per_block + (threadIdx.x >> 4); b < B;
+       b += kMulti ? B : (int64_t)gridDim.x * hw_per_block) {
+    const float pxf = x[b * stride], pyf = y[b * stride], thf = th[b * stride];
+    float snf, csf;
+    const bool th_ok = fabsf(thf) <= DT_SC_MAX;
+    dt_sincos_mufu(th_ok ? thf : 0.f, snf, csf);          // |error| <= DT_SC_ERR (carfast.cuh)
+    const float pxs = pxf * inv_s, pys = pyf * inv_s;
+    const float U0 = cys - pys - (snf + csf) * st_s, Uj = -snf * sp_s, Ui = -csf * sp_s;
+    const float W0 = cxs + pxs + (csf - snf) * st_s, Wj = csf * sp_s, Wi = -snf * sp_s;
+    // fp32 error bound of a lattice coordinate: as in k_local_map_fast (a coordinate is built from five roundings of
+    // the sixteen budgeted there)
+    const float mag = fabsf(pxs) + fabsf(pys) + span;
+    const float eps = 2.0f * (16.0f * 5.9604645e-8f * mag + 2.0f * DT_SC_ERR * ax.amax * inv_s) + 1.0e-7f;
+    const bool fast_ok = th_ok && reach_ok && eps < 0.25f && fabsf(pxs) <= 0.5f * (float)m.cols + 1.0f &&
+                         fabsf(pys) <= 0.5f * (float)m.rows + 1.0f;
+    const float lim = 0.5f - eps;
+    OutT* o = out + b * (int64_t)NN;
+    if (!fast_ok) {
+      // the lattice may leave the padded table (or the heading the MUFU range): the float64 code decides every point
+#pragma unroll 1
+      for (int qd = l16; qd < Q; qd += 16) {
+        const int i = qd / NQ, j = 4 * (qd - i * NQ);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = exact_value(thf, pxf, pyf, i, j + e);
+        store4(o, qd, v);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int qd = l16 + 16 * k;
+      if (16 * k + 15 < Q || qd < Q) {   // only the last iteration can be partial
+        float v[4], u[4], w[4], tu[4], tw[4], du[4], dw[4];
+        const float2 ij = s_ij[qd];
+        u[0] = fmaf(ij.x, Ui, fmaf(ij.y, Uj, U0));
+        w[0] = fmaf(ij.x, Wi, fmaf(ij.y, Wj, W0));
+#pragma unroll
+        for (int e = 1; e < 4; ++e) {
+          u[e] = fmaf((float)e, Uj, u[0]);
+          w[e] = fmaf((float)e, Wj, w[0]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          tu[e] = u[e] + MAGIC;
+          tw[e] = w[e] + MAGIC;
+          du[e] = u[e] - (tu[e] - MAGIC);   // distance to the cell centre: beyond 0.5 - eps a border is within the bound
+          dw[e] = w[e] - (tw[e] - MAGIC);
+        }
+        const float m0 = fmaxf(fmaxf(fabsf(du[0]), fabsf(dw[0])), fabsf(du[1]));
+        const float m1 = fmaxf(fmaxf(fabsf(dw[1]), fabsf(du[2])), fabsf(dw[2]));
+        const float m2 = fmaxf(fmaxf(fabsf(du[3]), fabsf(dw[3])), m0);
+        const bool amb = !(fmaxf(m1, m2) < lim);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // address = (bits(tu) * pitch + bits(tw)) * 4 + base, the magic constants' bits folded into the (wrapping) base
+          asm("{\n\t.reg .u32 t;\n\t"
+              "mad.lo.u32 t, %1, %2, %3;\n\t"
+              "shl.b32 t, t, 2;\n\t"
+              "add.u32 t, t, %4;\n\t"
+              "ld.shared.f32 %0, [t];\n\t}"
+              : "=f"(v[e])
+              : "r"(__float_as_uint(tu[e])), "r"(upitch), "r"(__float_as_uint(tw[e])), "r"(tab_u));
+        }
+        if (amb) {
+          const unsigned int slot = atomicAdd(&s_cnt, 1u);
+          if (slot < LMQ_CAP) {
+            s_list[slot] = (unsigned long long)b * (unsigned long long)Q + (unsigned long long)qd;
+          } else {   // list full: decide in line
+            const int i = qd / NQ, j = 4 * (qd - i * NQ);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = exact_value(thf, pxf, pyf, i, j + e);
+          }
+        }
+        store4(o, qd, v);
+      }
+    }
+  }
+  // ---- the listed quads: one float64 decision per thread, over the provisional values ----
+  __syncthreads();
+  const unsigned int n_list = s_cnt < (unsigned)LMQ_CAP ? s_cnt : (unsigned)LMQ_CAP;
+  for (unsigned int e = threadIdx.x; e < 4u * n_list; e += blockDim.x) {
+    const unsigned long long ent = s_list[e >> 2];
+    const int64_t b = (int64_t)(ent / (unsigned long long)Q);
+    const int qd = (int)(ent - (unsigned long long)b * (unsigned long long)Q);
+    const int i = qd / NQ, j = 4 * (qd - i * NQ) + (int)(e & 3u);
+    const float val = exact_value(th[b * stride], x[b * stride], y[b * stride], i, j);
+    OutT* o = out + b * (int64_t)NN + (i * NT + j);
+    if (sizeof(OutT) == 4) *reinterpret_cast<float*>(o) = val;
+    else *reinterpret_cast<__nv_bfloat16*>(o) = __float2bfloat16_rn(val);
+  }
+}
+
 // numpy.linspace(start, stop, N): arange(N) * step + start, last element forced to stop
 static Axis make_axis(int N, double scale) {
   Axis ax;
@@ -703,6 +904,27 @@ template <typename OutT, bool kMulti>
 static int local_map_fast_launch_t(dt_ctx* ctx, const MapView& m, const float* x, const float* y, const float* theta,
                                    int64_t stride, int64_t B, int N, const Axis& ax, OutT* out, const MultiMap& mm,
                                    int blocks, size_t smem, cudaStream_t st) {
+  // quads: the reference's map sizes (N = 20 car, 16 ant), 16- / 8-byte aligned output; multi-map launches are cut in
+  // blocks of 8 poses (one per warp) by the caller: the quad kernel takes 16 per block, so a group must hold a
+  // multiple of 16
+  const bool quad_ok = (N == 20 || N == 16) && (reinterpret_cast<uintptr_t>(out) & (sizeof(OutT) == 4 ? 15u : 7u)) == 0 &&
+                       (!kMulti || (mm.group_size % 16 == 0 && B % 16 == 0));
+  if (quad_ok) {
+    static bool qattr_done = false;
+    if (!qattr_done) {
+      DT_CUDA(cudaFuncSetAttribute(k_local_map_quad<OutT, kMulti, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      DT_CUDA(cudaFuncSetAttribute(k_local_map_quad<OutT, kMulti, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      qattr_done = true;
+    }
+    // two poses per warp; a single wave of resident blocks (LM_MINB per SM) strides over the poses: a second,
+    // partial wave would leave most SMs with one block
+    int qblocks = kMulti ? (int)(B / 16) : (int)((B + 15) / 16);
+    if (!kMulti && qblocks > ctx->sm_count * LM_MINB) qblocks = ctx->sm_count * LM_MINB;
+    if (N == 16) k_local_map_quad<OutT, kMulti, 16><<<qblocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, ax, out, mm);
+    else k_local_map_quad<OutT, kMulti, 20><<<qblocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, ax, out, mm);
+    DT_LAUNCH_CHECK("k_local_map_quad");
+    return DT_OK;
+  }
   const int it = (N * N + 63) / 64;
   static bool attr_done = false;
   if (!attr_done) {

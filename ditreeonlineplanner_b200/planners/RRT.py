@@ -190,8 +190,12 @@ class RRT_Planner(BasePlanner):
     def _local_map(self, state):
         n = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
         self._ctx = _ctx_for(self.maze, self.s_global)
-        pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None])
-        return self._ctx.local_map(pose, n, self.local_map_scale)
+        pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None]).to(self._ctx.device)
+        lm = self._ctx.local_map(pose, n, self.local_map_scale)
+        # the sampler wants the same map as 2 m - 1 in bf16 (fm_policy.py:152): made here by the same kernel (one launch
+        # instead of three element-wise ones per iteration) and handed over on the tensor
+        lm._ditree_signed_bf16 = self._ctx.local_map(pose, n, self.local_map_scale, bf16_signed=True)
+        return lm
 
     def _plan_device(self):
         """batch_mode = "device": the whole loop on the device (planners/device_planner.py, csrc/planner.cu) for this

@@ -120,11 +120,19 @@ class DiffusionSampler(nn.Module):
         if "car" in env:
             if self.obs_history != 1:
                 raise NotImplementedError("carmaze uses obs_history = 1")
-            last = np.ascontiguousarray(obs_seq[:, -1, :], dtype=np.float32)
-            prev = None if prev_actions is None else np.ascontiguousarray(prev_actions[:, -1, :], dtype=np.float32)
-            return ctx.build_cond_car(torch.as_tensor(last), None if prev is None else torch.as_tensor(prev),
-                                      torch.as_tensor(np.asarray(goal, dtype=np.float32)), self.metadata,
-                                      float(self.local_map_size))
+            # states | previous actions | goal(s) cross the bus as ONE array (three small copies cost 3 x ~10 us per
+            # call of the reference's B = 1 loop)
+            B = len(obs_seq)
+            g = np.asarray(goal, dtype=np.float32)
+            n_prev = 0 if prev_actions is None else 2 * B
+            flat = np.empty(6 * B + n_prev + g.size, dtype=np.float32)
+            flat[:6 * B] = obs_seq[:, -1, :].reshape(-1)
+            if n_prev:
+                flat[6 * B: 8 * B] = prev_actions[:, -1, :].reshape(-1)
+            flat[6 * B + n_prev:] = g.reshape(-1)
+            dev = torch.from_numpy(flat).to(ctx.device)
+            return ctx.build_cond_car(dev[:6 * B].view(B, 6), dev[6 * B: 8 * B].view(B, 2) if n_prev else None,
+                                      dev[6 * B + n_prev:].view(g.shape), self.metadata, float(self.local_map_size))
         if "ant" in env:
             seq = np.ascontiguousarray(obs_seq[:, -self.obs_history:, :], dtype=np.float32)
             prev = None if prev_actions is None else np.ascontiguousarray(prev_actions[:, -1, :], dtype=np.float32)
@@ -150,12 +158,16 @@ class DiffusionSampler(nn.Module):
         B = len(obs_seq)
         ctx = self._context()
         cond = self.build_cond(obs_seq, prev_actions, goal)
-        if isinstance(local_map, np.ndarray):
-            local_map = torch.from_numpy(local_map)
-        local_map = local_map.to(ctx.device, dtype=torch.float32)
-        if local_map.dim() == 2:
-            local_map = local_map.unsqueeze(0)
-        lm = (local_map * 2 - 1).to(torch.bfloat16)  # scale to [-1, 1] (fm_policy.py:152)
+        lm = getattr(local_map, "_ditree_signed_bf16", None)   # create_local_map's device result carries the encoder's
+        if lm is None or lm.device != ctx.device:              # form of the same map (2 m - 1, bf16) when it made it
+            if isinstance(local_map, np.ndarray):
+                local_map = torch.from_numpy(local_map)
+            local_map = local_map.to(ctx.device, dtype=torch.float32)
+            if local_map.dim() == 2:
+                local_map = local_map.unsqueeze(0)
+            lm = (local_map * 2 - 1).to(torch.bfloat16)  # scale to [-1, 1] (fm_policy.py:152)
+        elif lm.dim() == 2:
+            lm = lm.unsqueeze(0)
         if noise is None:
             noise = torch.randn((B, self.pred_horizon, self.action_dim), device=ctx.device)
         naction = ctx.fm_sample(noise, cond, lm, self.num_diffusion_iters)

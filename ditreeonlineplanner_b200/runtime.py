@@ -227,7 +227,7 @@ class Context:
 
     # -- dynamics ---------------------------------------------------------------------------
     def propagate_collide(self, state0, actions, goal_xy, S=None, want_traj=True, soa=False,
-                          stop_on_collision=True):
+                          stop_on_collision=True, packed_out=False):
         """state0: (B,6) rows, or (6,B) when soa.  actions: (B,T,2) rows (T >= S), or (S,2,B) when soa.
         Returns dict(traj, final, first_coll, done_step); traj is (B,S,6) rows or (S,6,B) when soa."""
         s0 = self._f32(state0)
@@ -260,11 +260,22 @@ class Context:
             t_str = (pitch, 6, 1)
         first = torch.empty(B, dtype=torch.int32, device=self.device)
         done = torch.empty(B, dtype=torch.int32, device=self.device)
+        if packed_out and not soa and want_traj:
+            # one allocation [traj rows | final | first | done] so that a caller who needs everything on the host (the
+            # reference's B = 1 loop) fetches it with ONE device->host copy instead of four
+            blob = torch.empty(B * pitch + B * 8, dtype=torch.float32, device=self.device)
+            traj = blob[: B * pitch].view(B, pitch)[:, : S * 6].unflatten(1, (S, 6))
+            final = blob[B * pitch: B * pitch + B * 6].view(B, 6)
+            first = blob[B * pitch + B * 6: B * pitch + B * 7].view(torch.int32)
+            done = blob[B * pitch + B * 7:].view(torch.int32)
         self._check(self.lib.dt_propagate_collide(
             self.h, _ptr(s0), s_str[0], s_str[1], _ptr(act), a_str[0], a_str[1], a_str[2], B, int(S),
             float(goal_xy[0]), float(goal_xy[1]), _ptr(traj), t_str[0], t_str[1], t_str[2], _ptr(final), _ptr(first),
             _ptr(done), L.DT_PROP_STOP_ON_COLLISION if stop_on_collision else 0, self._stream()))
-        return dict(traj=traj, final=final, first_coll=first, done_step=done)
+        res = dict(traj=traj, final=final, first_coll=first, done_step=done)
+        if packed_out and not soa and want_traj:
+            res["blob"], res["pitch"] = blob, pitch
+        return res
 
     # -- conditioning -----------------------------------------------------------------------
     def build_cond_car(self, states, prev_action, goal, meta, map_size=20.0):
@@ -482,6 +493,7 @@ class Context:
 
 
 _default = {}
+_cuda_ok = False
 
 
 def get_context(device=None):
@@ -489,8 +501,11 @@ def get_context(device=None):
     ``device=None`` means torch's current CUDA device, so one-process-per-GPU launches (torchrun sets
     the device from LOCAL_RANK) get the context of their own GPU."""
     if device is None:
-        if not torch.cuda.is_available():
-            raise RuntimeError("ditreeonlineplanner_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        global _cuda_ok
+        if not _cuda_ok:   # checked until it succeeds once (torch.cuda.is_available() costs 5 us a call: NVML + getenv)
+            if not torch.cuda.is_available():
+                raise RuntimeError("ditreeonlineplanner_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+            _cuda_ok = True
         device = torch.cuda.current_device()
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)
     if idx not in _default:

@@ -85,7 +85,7 @@ struct dt_denoiser {
   __nv_bfloat16* g_lm = nullptr;  // [GB][NM][NM]
   float* g_out = nullptr;      // [GB][T][A]
   struct GraphEntry { int B, K; unsigned ebits; int norm; int state; /* 0 seen once, 1 graph, -1 not capturable */
-                      cudaGraphExec_t exec; long long launches; };
+                      cudaGraphExec_t exec; long long launches; float* film_table; /* [K][F], filled at capture time */ };
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   float* norm_dev = nullptr;   // [2 A] action mean / std on the device, cached (dt_fm_sample)
@@ -232,6 +232,16 @@ __global__ void k_film_input(const float* __restrict__ emb, int emb_ld, int E, c
     else if (c < E + G) v = mishf(cond[b * G + (c - E)]);
     out[i] = __float2bfloat16(v);
   }
+}
+
+// three word-wise copies in one launch (the inputs of a graph-replayed sampler call into its static buffers)
+__global__ void k_stage3(const uint32_t* __restrict__ s0, uint32_t* __restrict__ d0, size_t n0,
+                         const uint32_t* __restrict__ s1, uint32_t* __restrict__ d1, size_t n1,
+                         const uint32_t* __restrict__ s2, uint32_t* __restrict__ d2, size_t n2) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n0) d0[i] = s0[i];
+  else if (i < n0 + n1) d1[i - n0] = s1[i - n0];
+  else if (i < n0 + n1 + n2) d2[i - n0 - n1] = s2[i - n0 - n1];
 }
 
 // time MLP for all K steps: Mish(Linear(Mish(Linear(sinusoid(t_k))))) -> mish_t[k][256]
@@ -582,15 +592,19 @@ static TT* arena(dt_denoiser* d, size_t n, bool* ok) {
 // captured sampler graphs bake in the kernel selection: dropped whenever an option that changes it is set
 void dt_denoiser_drop_graphs(dt_ctx* ctx) {
   if (!ctx || !ctx->den) return;
-  for (auto& g : ctx->den->graphs)
+  for (auto& g : ctx->den->graphs) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.film_table) cudaFree(g.film_table);
+  }
   ctx->den->graphs.clear();
 }
 
 void dt_denoiser_free(dt_ctx* ctx) {
   if (!ctx || !ctx->den) return;
-  for (auto& g : ctx->den->graphs)
+  for (auto& g : ctx->den->graphs) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.film_table) cudaFree(g.film_table);
+  }
   if (ctx->den->cap_stream) cudaStreamDestroy(ctx->den->cap_stream);
   for (void* p : ctx->den->allocs) cudaFree(p);
   delete ctx->den;
@@ -1176,11 +1190,13 @@ static int film_candidates(dt_ctx* ctx, dt_denoiser* d, const float* emb, int em
   return dt_conv_gemm(ctx, g, st);
 }
 
-static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, cudaStream_t st, bool force = false) {
+static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, cudaStream_t st,
+                      float* private_table = nullptr) {
   // The per-step FiLM table depends only on the timesteps and the weights: an unchanged schedule (every call
   // of a planner run) reuses the table of the previous call -- stream order makes that safe on one stream;
-  // a different stream recomputes.
-  if (!force && d->film_time_K == K && d->film_time_stream == (void*)st &&
+  // a different stream recomputes.  `private_table`: compute into the caller's own [K][F] buffer instead (a
+  // captured graph keeps one per schedule, filled once at capture time, so that its replays skip these launches).
+  if (!private_table && d->film_time_K == K && d->film_time_stream == (void*)st &&
       memcmp(d->film_time_ts, ts_host, K * sizeof(float)) == 0)
     return DT_OK;
   TimeSteps ts;
@@ -1190,8 +1206,10 @@ static int film_times(dt_ctx* ctx, dt_denoiser* d, const float* ts_host, int K, 
   DT_LAUNCH_CHECK("k_time_mlp1");
   dt_launch(ctx->pdl_on, k_time_mlp2, K * 32, 256, 0, st, d->time_h, d->t_w2, d->t_b2, d->mish_t);
   DT_LAUNCH_CHECK("k_time_mlp2");
-  dt_launch(ctx->pdl_on, k_film_time, (d->F + 7) / 8, 256, 0, st, d->film_wt, d->mish_t, d->F, K, d->film_time);
+  dt_launch(ctx->pdl_on, k_film_time, (d->F + 7) / 8, 256, 0, st, d->film_wt, d->mish_t, d->F, K,
+            private_table ? private_table : d->film_time);
   DT_LAUNCH_CHECK("k_film_time");
+  if (private_table) return DT_OK;
   d->film_time_K = K;
   d->film_time_stream = (void*)st;
   memcpy(d->film_time_ts, ts_host, K * sizeof(float));
@@ -1247,9 +1265,11 @@ extern "C" int dt_unet_forward(dt_ctx* ctx, const float* sample, const float* em
 // encoder once, per-candidate FiLM once, then K Euler steps of the U-Net (fm_policy.py:183-194)
 static int fm_sample_body(dt_ctx* ctx, dt_denoiser* d, const float* noise, const float* cond, const __nv_bfloat16* lm,
                           int64_t B, int K, const float* ts, const float* dt, const float* d_norm, float* actions_out,
-                          cudaStream_t st, bool force_film_times) {
-  int rc = film_times(ctx, d, ts, K, st, force_film_times);
+                          cudaStream_t st, const float* film_table) {
+  // film_table: a ready per-step FiLM table [K][F] (a captured graph's own); null: the context's, refreshed if stale
+  int rc = film_table ? DT_OK : film_times(ctx, d, ts, K, st);
   if (rc) return rc;
+  if (!film_table) film_table = d->film_time;
   for (int64_t b0 = 0; b0 < B; b0 += d->MB) {
     const int64_t nb = (B - b0 < d->MB) ? (B - b0) : d->MB;
     const int64_t rows = nb * d->T;
@@ -1261,7 +1281,7 @@ static int fm_sample_body(dt_ctx* ctx, dt_denoiser* d, const float* noise, const
       // (k == 0 follows the copy of the noise: a memcpy node is no programmatic-launch primary)
       dt_launch(ctx->pdl_on && k > 0, k_prep_sample, ew_grid(rows * 64, ctx), 256, 0, st, a, rows, d->A, d->X);
       DT_LAUNCH_CHECK("k_prep_sample");
-      if ((rc = unet_body(ctx, d, nb, d->film_time + (size_t)k * d->F, st))) return rc;
+      if ((rc = unet_body(ctx, d, nb, film_table + (size_t)k * d->F, st))) return rc;
       if ((rc = launch_final_euler(ctx, d->F0, rows, d->C[0], d->A, d->final_w, d->final_b, dt[k], a, nullptr,
                                    (k == K - 1) ? d_norm : nullptr, st)))
         return rc;
@@ -1325,21 +1345,41 @@ extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, 
     for (auto& g : d->graphs)
       if (g.B == (int)B && g.K == K && g.ebits == ebits && g.norm == (d_norm != nullptr)) ge = &g;
     if (!ge) {  // first call with this key: eager (runs first-use initialisation), remembered
-      d->graphs.push_back(dt_denoiser::GraphEntry{(int)B, K, ebits, d_norm != nullptr, 0, nullptr, 0});
+      d->graphs.push_back(dt_denoiser::GraphEntry{(int)B, K, ebits, d_norm != nullptr, 0, nullptr, 0, nullptr});
     } else if (ge->state >= 0) {
       const size_t na = (size_t)B * d->T * d->A;
-      DT_CUDA(cudaMemcpyAsync(d->g_noise, noise, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      DT_CUDA(cudaMemcpyAsync(d->g_cond, cond, (size_t)B * d->G * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      DT_CUDA(cudaMemcpyAsync(d->g_lm, lm, (size_t)B * d->NM * d->NM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+      {
+        // the three inputs move into the graph's static buffers with one launch (three copy nodes cost ~3 us each)
+        const size_t w0 = na, w1 = (size_t)B * d->G, w2 = ((size_t)B * d->NM * d->NM * sizeof(__nv_bfloat16) + 3) / 4;
+        const size_t words = w0 + w1 + w2;
+        if ((((uintptr_t)lm | (uintptr_t)d->g_lm) & 3) != 0 || ((size_t)B * d->NM * d->NM) % 2 != 0) {
+          DT_CUDA(cudaMemcpyAsync(d->g_noise, noise, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+          DT_CUDA(cudaMemcpyAsync(d->g_cond, cond, (size_t)B * d->G * sizeof(float), cudaMemcpyDeviceToDevice, st));
+          DT_CUDA(cudaMemcpyAsync(d->g_lm, lm, (size_t)B * d->NM * d->NM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+        } else {
+          k_stage3<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(
+              (const uint32_t*)noise, (uint32_t*)d->g_noise, w0, (const uint32_t*)cond, (uint32_t*)d->g_cond, w1,
+              (const uint32_t*)lm, (uint32_t*)d->g_lm, w2);
+          DT_LAUNCH_CHECK("k_stage3");
+        }
+      }
       if (ge->state == 0) {
-        const long long l0 = ctx->launches;
         cudaGraph_t graph = nullptr;
         // captured on a private stream (the caller's may be the legacy default stream, which cannot be
         // captured); the instantiated graph is then launched into the caller's stream
         if (!d->cap_stream) cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking);
-        bool ok = d->cap_stream && cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        // this schedule's per-step FiLM table: computed once, here, on the caller's stream (every replay is enqueued
+        // behind it), so the graph itself holds no time-MLP launches
+        if (!ge->film_table && cudaMalloc(&ge->film_table, (size_t)K * d->F * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          ge->film_table = nullptr;
+        }
+        bool ok = ge->film_table != nullptr && film_times(ctx, d, ts, K, st, ge->film_table) == DT_OK;
+        const long long l0 = ctx->launches;   // launches of one replay = what the capture records
+        ok = ok && d->cap_stream && cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
         if (ok) {
-          rc = fm_sample_body(ctx, d, d->g_noise, d->g_cond, d->g_lm, B, K, ts, dt, d_norm, d->g_out, d->cap_stream, true);
+          rc = fm_sample_body(ctx, d, d->g_noise, d->g_cond, d->g_lm, B, K, ts, dt, d_norm, d->g_out, d->cap_stream,
+                              ge->film_table);
           const cudaError_t e = cudaStreamEndCapture(d->cap_stream, &graph);
           ok = (rc == DT_OK) && (e == cudaSuccess) && graph != nullptr;
         }
@@ -1358,14 +1398,10 @@ extern "C" int dt_fm_sample(dt_ctx* ctx, const float* noise, const float* cond, 
       if (ge->state == 1) {
         DT_CUDA(cudaGraphLaunch(ge->exec, st));
         ctx->launches += ge->launches;
-        // the graph recomputed the per-step FiLM table for ITS schedule: record what the table now holds
-        d->film_time_K = K;
-        d->film_time_stream = (void*)st;
-        memcpy(d->film_time_ts, ts, K * sizeof(float));
         DT_CUDA(cudaMemcpyAsync(actions_out, d->g_out, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return DT_OK;
       }
     }
   }
-  return fm_sample_body(ctx, d, noise, cond, lm, B, K, ts, dt, d_norm, actions_out, st, false);
+  return fm_sample_body(ctx, d, noise, cond, lm, B, K, ts, dt, d_norm, actions_out, st, nullptr);
 }

@@ -190,11 +190,15 @@ class RRT_Planner(BasePlanner):
     def _local_map(self, state):
         n = int(self.local_map_size) if isinstance(self.local_map_size, (int, float)) else int(self.local_map_size[0])
         self._ctx = _ctx_for(self.maze, self.s_global)
-        pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None]).to(self._ctx.device)
-        lm = self._ctx.local_map(pose, n, self.local_map_scale)
-        # the sampler wants the same map as 2 m - 1 in bf16 (fm_policy.py:152): made here by the same kernel (one launch
-        # instead of three element-wise ones per iteration) and handed over on the tensor
-        lm._ditree_signed_bf16 = self._ctx.local_map(pose, n, self.local_map_scale, bf16_signed=True)
+        pose = torch.as_tensor(np.asarray(state[:3], dtype=np.float32)[None])
+        # the planning loops hand this map to the sampler only, which wants it as 2 m - 1 in bf16 (fm_policy.py:152): the
+        # kernel writes that form directly (one launch instead of the map plus three element-wise kernels per iteration)
+        # and marks the tensor so that DiffusionSampler.forward takes it as is; common.map_utils.create_local_map is the
+        # reference-shaped ({0, 1} float) entry point
+        if not getattr(self.sampler, "_accepts_signed_bf16_map", False):
+            return self._ctx.local_map(pose, n, self.local_map_scale)   # any other sampler: the reference's {0, 1} map
+        lm = self._ctx.local_map(pose, n, self.local_map_scale, bf16_signed=True)
+        lm._ditree_signed_bf16 = True
         return lm
 
     def _plan_device(self):

@@ -180,7 +180,8 @@ class BasePlanner(abc.ABC):
         pitch = res["pitch"]
         first, done_step = int(host[pitch + 6: pitch + 7].view(np.int32)[0]), int(host[pitch + 7: pitch + 8].view(np.int32)[0])
         traj = host[: n * 6].reshape(n, 6).astype(np.float64)
-        ctx.sync_status()
+        if self.maze.shape[0] > self.maze.shape[1]:
+            ctx.sync_status()   # IndexError like the reference's clipped diagonal lookup: only tall maps can raise it
         obs = host[pitch: pitch + 6].astype(np.float64)
         self.env.set_state(obs.copy())
         self.env.current_step += (first + 1) if first >= 0 else ((done_step + 1) if done_step >= 0 else n)

@@ -70,6 +70,8 @@ class DiffusionSampler(nn.Module):
         self._ctx = None
         self._key = None
 
+    _accepts_signed_bf16_map = True   # forward() takes the planners' pre-scaled bf16 local map (RRT_Planner._local_map)
+
     # nn.Module.to()/eval() keep working; the packed weights live in the device context
     def _context(self):
         """The process-wide device context with THIS sampler's weights packed in it.  Contexts are shared per
@@ -113,9 +115,9 @@ class DiffusionSampler(nn.Module):
                 or not self.local_map_conditioned or self.action_history != 1:
             raise NotImplementedError("the B200 path implements the reference's carmaze/antmaze 'actions' configuration")
 
-    def build_cond(self, obs_seq, prev_actions, goal):
+    def build_cond(self, obs_seq, prev_actions, goal, ctx=None):
         """Condition vectors (B,G) on the device (fm_policy.py:71-143)."""
-        ctx = self._context()
+        ctx = ctx if ctx is not None else self._context()
         env = self.env_id.lower()
         if "car" in env:
             if self.obs_history != 1:
@@ -157,9 +159,12 @@ class DiffusionSampler(nn.Module):
                 prev_actions = prev_actions[None]
         B = len(obs_seq)
         ctx = self._context()
-        cond = self.build_cond(obs_seq, prev_actions, goal)
-        lm = getattr(local_map, "_ditree_signed_bf16", None)   # create_local_map's device result carries the encoder's
-        if lm is None or lm.device != ctx.device:              # form of the same map (2 m - 1, bf16) when it made it
+        cond = self.build_cond(obs_seq, prev_actions, goal, ctx)
+        lm = None
+        if getattr(local_map, "_ditree_signed_bf16", False) and local_map.dtype == torch.bfloat16 \
+                and local_map.device == ctx.device:
+            lm = local_map                                     # already 2 m - 1 in bf16 (the planners' _local_map)
+        if lm is None:
             if isinstance(local_map, np.ndarray):
                 local_map = torch.from_numpy(local_map)
             local_map = local_map.to(ctx.device, dtype=torch.float32)

@@ -249,17 +249,15 @@ class Context:
             assert S <= act.shape[1]
             s_str = (6, 1)
             a_str = (act.stride(0), act.stride(1), 1)
-            final = torch.empty_like(s0)
+            final = None if (packed_out and want_traj) else torch.empty_like(s0)
             # (B, S, 6) rows; the row pitch is padded to a whole number of 32-byte sectors so that every
             # 4-step piece the kernel writes covers complete sectors (1200-byte rows would leave every other
             # row straddling them: partial-sector writes cost L2 read-modify-writes)
             pitch = -(-(S * 6) // 8) * 8
             traj = None
-            if want_traj:
+            if want_traj and not packed_out:
                 traj = torch.empty((B, pitch), dtype=torch.float32, device=self.device)[:, : S * 6].unflatten(1, (S, 6))
             t_str = (pitch, 6, 1)
-        first = torch.empty(B, dtype=torch.int32, device=self.device)
-        done = torch.empty(B, dtype=torch.int32, device=self.device)
         if packed_out and not soa and want_traj:
             # one allocation [traj rows | final | first | done] so that a caller who needs everything on the host (the
             # reference's B = 1 loop) fetches it with ONE device->host copy instead of four
@@ -268,6 +266,9 @@ class Context:
             final = blob[B * pitch: B * pitch + B * 6].view(B, 6)
             first = blob[B * pitch + B * 6: B * pitch + B * 7].view(torch.int32)
             done = blob[B * pitch + B * 7:].view(torch.int32)
+        else:
+            first = torch.empty(B, dtype=torch.int32, device=self.device)
+            done = torch.empty(B, dtype=torch.int32, device=self.device)
         self._check(self.lib.dt_propagate_collide(
             self.h, _ptr(s0), s_str[0], s_str[1], _ptr(act), a_str[0], a_str[1], a_str[2], B, int(S),
             float(goal_xy[0]), float(goal_xy[1]), _ptr(traj), t_str[0], t_str[1], t_str[2], _ptr(final), _ptr(first),

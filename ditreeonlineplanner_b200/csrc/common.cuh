@@ -55,6 +55,9 @@ struct dt_ctx {
   void* d_wide = nullptr;  // fp32 pre-normalisation scratch of the wide-GroupNorm GEMM fallback (gemm.cu)
   size_t wide_bytes = 0;
   void* d_splitk = nullptr;   // fixed-size fp32 scratch of the split-K path (gemm.cu)
+  void* d_splitk2 = nullptr;  // the same for layers running concurrently on the denoiser's side stream
+  bool pdl_now = true;        // pdl_on && this launch's ConvGemm::pdl (set by dt_conv_gemm)
+  bool fork_on = true;        // dt_set_option(ctx, "fork", 0): no side stream for the residual 1 x 1 convs
   bool splitk_on = true;      // dt_set_option(ctx, "splitk", 0) restores batch-size independent bits
   // programmatic dependent launch for the denoiser's kernel chain (dt_set_option(ctx, "pdl", 0) or DITREE_PDL=0
   // turn it off): a kernel's CTAs are scheduled, and run their prologue (barrier init, TMEM allocation, tensor-map

@@ -21,6 +21,8 @@ extern "C" int dt_ctx_create(int device, dt_ctx** out) {
   {
     const char* e = getenv("DITREE_PDL");
     if (e && e[0] == '0') ctx->pdl_on = false;
+    e = getenv("DITREE_FORK");
+    if (e && e[0] == '0') ctx->fork_on = false;
   }
   if (prop.major != 10) {
     // sm_100a cubins only load on compute capability 10.x parts; fail loudly instead of later
@@ -54,6 +56,7 @@ extern "C" void dt_ctx_destroy(dt_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_wide) cudaFree(ctx->d_wide);
   if (ctx->d_splitk) cudaFree(ctx->d_splitk);
+  if (ctx->d_splitk2) cudaFree(ctx->d_splitk2);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   delete ctx;
 }
@@ -67,6 +70,15 @@ extern "C" int dt_set_option(dt_ctx* ctx, const char* name, int value) {
       dt_denoiser_drop_graphs(ctx);
     }
     ctx->splitk_on = value != 0;
+    return DT_OK;
+  }
+  if (strcmp(name, "fork") == 0) {
+    if (ctx->fork_on != (value != 0)) {  // captured graphs hold the fork / join edges
+      DT_CUDA(cudaSetDevice(ctx->device));
+      DT_CUDA(cudaDeviceSynchronize());
+      dt_denoiser_drop_graphs(ctx);
+    }
+    ctx->fork_on = value != 0;
     return DT_OK;
   }
   if (strcmp(name, "pdl") == 0) {

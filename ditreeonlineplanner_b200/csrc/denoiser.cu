@@ -23,6 +23,7 @@
 #include "gemm.cuh"
 
 #define DEN_KMAX 64  // max ODE steps per call
+#define DEN_FORK_MAXB 128   // side-stream forks up to this batch (measured: -7 % at 1, -5 % at 64, +1 % at 256)
 #define DEN_GRAPH_MAXB 256  // sampler calls up to this batch are replayed as CUDA graphs (host cost ~0.3 -> 0.05 ms)
 
 // ------------------------------------------------------------------------------------------
@@ -87,6 +88,10 @@ struct dt_denoiser {
   struct GraphEntry { int B, K; unsigned ebits; int norm; int state; /* 0 seen once, 1 graph, -1 not capturable */
                       cudaGraphExec_t exec; long long launches; float* film_table; /* [K][F], filled at capture time */ };
   std::vector<GraphEntry> graphs;
+  // side stream of small-batch passes: a residual block's 1 x 1 residual conv runs beside its first 3-tap conv
+  // (fork / join by events; inside a captured graph these become parallel branches)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t cap_stream = nullptr;
   float* norm_dev = nullptr;   // [2 A] action mean / std on the device, cached (dt_fm_sample)
   float norm_host[16];
@@ -606,6 +611,9 @@ void dt_denoiser_free(dt_ctx* ctx) {
     if (g.film_table) cudaFree(g.film_table);
   }
   if (ctx->den->cap_stream) cudaStreamDestroy(ctx->den->cap_stream);
+  if (ctx->den->side) cudaStreamDestroy(ctx->den->side);
+  if (ctx->den->ev_fork) cudaEventDestroy(ctx->den->ev_fork);
+  if (ctx->den->ev_join) cudaEventDestroy(ctx->den->ev_join);
   for (void* p : ctx->den->allocs) cudaFree(p);
   delete ctx->den;
   ctx->den = nullptr;
@@ -880,10 +888,40 @@ static int conv_s1(dt_ctx* ctx, const ConvW& w, int k, Act in0, const Act* in1, 
   return dt_conv_gemm(ctx, g, st);
 }
 
+// the side stream and its fork / join events (created on first use); false when forking is off or unavailable
+static bool side_stream_ready(dt_ctx* ctx, dt_denoiser* d) {
+  if (!ctx->fork_on || ctx->prof_on) return false;
+  if (!d->side) {
+    if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->fork_on = false;
+      return false;
+    }
+  }
+  return true;
+}
+
 static int res_block(dt_ctx* ctx, dt_denoiser* d, const ResBlockW& rb, Act in0, const Act* in1, int64_t B,
                      const float* film_t_k, __nv_bfloat16* H, __nv_bfloat16* R, __nv_bfloat16* out, cudaStream_t st) {
   const int T = in0.T;
   int rc;
+  // Small batches (every launch is latency-bound, the SMs are mostly idle): the 1 x 1 residual conv does not depend
+  // on the block's first conv, so it runs on a side stream beside it and joins before the second conv's epilogue
+  // reads it.  Its launches carry no programmatic-launch attribute (their predecessor is an event, not a kernel).
+  const bool fork = rb.has_res && B <= DEN_FORK_MAXB && side_stream_ready(ctx, d);
+  if (fork) {
+    DT_CUDA(cudaEventRecord(d->ev_fork, st));
+    DT_CUDA(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+    ConvGemm gr;
+    gr.epi = EPI_PLAIN;
+    gr.out_bf16 = R;
+    gr.pdl = false;
+    gr.scratch = 1;
+    if ((rc = conv_s1(ctx, rb.res, 1, in0, in1, B, gr, d->side))) return rc;
+    DT_CUDA(cudaEventRecord(d->ev_join, d->side));
+  }
   // h = FiLM(Mish(GN(conv3(x))))                         conditional_unet1d.py:111-120
   ConvGemm g1;
   g1.epi = EPI_GN_MISH;
@@ -897,7 +935,10 @@ static int res_block(dt_ctx* ctx, dt_denoiser* d, const ResBlockW& rb, Act in0, 
   if ((rc = conv_s1(ctx, rb.c1, 3, in0, in1, B, g1, st))) return rc;
   // residual path                                          conditional_unet1d.py:100-101,141
   const __nv_bfloat16* resid;
-  if (rb.has_res) {
+  if (fork) {
+    DT_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+    resid = R;
+  } else if (rb.has_res) {
     ConvGemm gr;
     gr.epi = EPI_PLAIN;
     gr.out_bf16 = R;
@@ -915,6 +956,7 @@ static int res_block(dt_ctx* ctx, dt_denoiser* d, const ResBlockW& rb, Act in0, 
   g2.resid = resid;
   g2.ld_res = rb.cout;
   g2.out_bf16 = out;
+  g2.pdl = !fork;   // after a join the predecessors are a kernel AND an event: plain full dependencies
   Act h{H, T, rb.cout};
   return conv_s1(ctx, rb.c2, 3, h, nullptr, B, g2, st);
 }
@@ -1035,12 +1077,16 @@ static int gn2d(dt_ctx* ctx, const ConvW& w, __nv_bfloat16* x, int64_t B, int HW
   return DT_OK;
 }
 
+// `after_event`: this launch does not follow a kernel of the chain in its stream (it runs on the side stream, or right
+// after a join): no programmatic-launch attribute; side-stream launches also take the second split-K scratch
 static int enc_conv_gn(dt_ctx* ctx, dt_denoiser* d, const ConvW& w, const __nv_bfloat16* in, int64_t B, int H, int W,
                        int Cin, int k, int stride, int pad, int OH, int OW, const __nv_bfloat16* resid, int relu,
-                       __nv_bfloat16* out, cudaStream_t st) {
+                       __nv_bfloat16* out, cudaStream_t st, bool after_event = false, bool side = false) {
   const int64_t rows = B * OH * OW;
   const int T = OH * OW;
   ConvGemm g;
+  g.pdl = !after_event;
+  g.scratch = side ? 1 : 0;
   g.n_src = 1;
   g.w = w.w;
   g.N = w.N;
@@ -1131,16 +1177,31 @@ static int encoder_forward(dt_ctx* ctx, dt_denoiser* d, const __nv_bfloat16* lm,
     for (int b = 0; b < 2; ++b) {
       const EncBlockW& eb = d->enc[li][b];
       const int OH = (H + 2 - 3) / eb.stride + 1;
+      // identity / downsample branch: gn(conv1x1(x)) -- beside conv1 on the side stream at small batches (as the
+      // U-Net's residual convs, res_block), when it takes the TMA-addressed path (no shared im2col scratch)
+      const __nv_bfloat16* idt = cur;
+      bool joined = false;
+      if (eb.has_ds) {
+        const bool fork = B <= DEN_FORK_MAXB && OH * OH <= 128 && eb.cin % 64 == 0 && eb.ds.N % 64 == 0 &&
+                          eb.ds.Ktot == eb.cin && side_stream_ready(ctx, d);
+        if (fork) {
+          DT_CUDA(cudaEventRecord(d->ev_fork, st));
+          DT_CUDA(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+          if ((rc = enc_conv_gn(ctx, d, eb.ds, cur, B, H, H, eb.cin, 1, eb.stride, 0, OH, OH, nullptr, 0, t3, d->side, true, true)))
+            return rc;
+          DT_CUDA(cudaEventRecord(d->ev_join, d->side));
+          joined = true;
+        }
+      }
       // y = relu(gn(conv1(x)))
       if ((rc = enc_conv_gn(ctx, d, eb.c1, cur, B, H, H, eb.cin, 3, eb.stride, 1, OH, OH, nullptr, 1, t1, st))) return rc;
-      // identity / downsample branch: gn(conv1x1(x))
-      const __nv_bfloat16* idt = cur;
       if (eb.has_ds) {
-        if ((rc = enc_conv_gn(ctx, d, eb.ds, cur, B, H, H, eb.cin, 1, eb.stride, 0, OH, OH, nullptr, 0, t3, st))) return rc;
+        if (joined) DT_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+        else if ((rc = enc_conv_gn(ctx, d, eb.ds, cur, B, H, H, eb.cin, 1, eb.stride, 0, OH, OH, nullptr, 0, t3, st))) return rc;
         idt = t3;
       }
       // out = relu(gn(conv2(y)) + identity)
-      if ((rc = enc_conv_gn(ctx, d, eb.c2, t1, B, OH, OH, eb.cout, 3, 1, 1, OH, OH, idt, 1, t2, st))) return rc;
+      if ((rc = enc_conv_gn(ctx, d, eb.c2, t1, B, OH, OH, eb.cout, 3, 1, 1, OH, OH, idt, 1, t2, st, joined))) return rc;
       __nv_bfloat16* nxt = t2;
       t2 = cur;
       cur = nxt;

@@ -1108,7 +1108,7 @@ static int launch_gemm_cg(dt_ctx* ctx, const CUtensorMap& a0, const CUtensorMap&
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl_on ? 2 : 1;
+  cfg.numAttrs = ctx->pdl_now ? 2 : 1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->prof_on) {
     e0 = dt_prof_event(ctx);
@@ -1398,8 +1398,9 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   ksplit = (int)((nkb + per - 1) / per);             // no empty slice
   if (g.epi != EPI_PLAIN && (g.group_width < 8 || g.N % g.group_width != 0 || g.group_width * g.T > 16384)) return 0;
   if ((size_t)ksplit * rows * g.N * sizeof(float) > SPLITK_SCRATCH_BYTES) return 0;
-  if (!ctx->d_splitk) {  // fixed size, allocated once: the pointer is baked into captured graphs
-    DT_CUDA(cudaMalloc(&ctx->d_splitk, SPLITK_SCRATCH_BYTES));
+  void*& scratch = g.scratch ? ctx->d_splitk2 : ctx->d_splitk;
+  if (!scratch) {  // fixed size, allocated once: the pointer is baked into captured graphs
+    DT_CUDA(cudaMalloc(&scratch, SPLITK_SCRATCH_BYTES));
     DT_CUDA(cudaFuncSetAttribute(k_splitk_epi, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
   }
   ConvGemm part = g;
@@ -1407,13 +1408,14 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   part.bias = nullptr; part.gamma = part.beta = nullptr; part.film = part.film_t = nullptr;
   part.resid = nullptr; part.relu = 0;
   part.out_bf16 = nullptr;
-  part.out_f32 = (float*)ctx->d_splitk;
+  part.out_f32 = (float*)scratch;
   part.ldc = g.N; part.out_b_stride = g.T; part.out_t_stride = 1; part.out_off = 0;
   part.ksplit = ksplit; part.kb_per_slice = per; part.slice_rows = rows;
   int rc = dt_conv_gemm(ctx, part, st);
   if (rc) return rc;
+  ctx->pdl_now = ctx->pdl_on;  // the reduction always follows its own GEMM in the stream
   SplitKEpi e;
-  e.part = (const float*)ctx->d_splitk; e.S = ksplit; e.rows = rows; e.T = g.T; e.N = g.N; e.epi = g.epi; e.relu = g.relu;
+  e.part = (const float*)scratch; e.S = ksplit; e.rows = rows; e.T = g.T; e.N = g.N; e.epi = g.epi; e.relu = g.relu;
   e.gw = (g.epi != EPI_PLAIN) ? g.group_width : 64;
   e.bias = g.bias; e.gamma = g.gamma; e.beta = g.beta; e.film = g.film; e.film_ld = g.film_ld; e.film_t = g.film_t;
   e.resid = g.resid; e.ld_res = g.ld_res; e.out_bf16 = g.out_bf16; e.out_f32 = g.out_f32;
@@ -1445,7 +1447,7 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl_on ? 2 : 1;
+  cfg.numAttrs = ctx->pdl_now ? 2 : 1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->prof_on) {  // the reduction is part of the layer's cost: recorded as epi = 2 (no flops of its own)
     e0 = dt_prof_event(ctx);
@@ -1464,6 +1466,7 @@ static int conv_gemm_splitk(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
 
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st) {
   if (g.B <= 0) return DT_OK;
+  ctx->pdl_now = ctx->pdl_on && g.pdl;
   if (g.nseg < 1 || g.nseg > GEMM_MAX_SEG || !g.w || !g.a[0].ptr || g.N % 64 != 0)
     return dt_fail(ctx, DT_E_ARG, "dt_conv_gemm: bad problem description");
   {

@@ -65,6 +65,10 @@ struct ConvGemm {
   // ---- split-K (set by dt_conv_gemm itself for small problems; plain epilogue, fp32 partial sums) -------
   int ksplit = 1, kb_per_slice = 0;
   int64_t slice_rows = 0;
+  // ---- launch ------------------------------------------------------------------------------------
+  bool pdl = true;   // programmatic dependent launch (if the context allows it): off for a launch whose predecessor in
+                     // its stream is not a kernel of this chain (after an event wait / on the side stream)
+  int scratch = 0;   // which split-K scratch buffer (a layer running on the side stream takes its own: 1)
 };
 
 int dt_conv_gemm(dt_ctx* ctx, const ConvGemm& g, cudaStream_t st);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of programmatic dependent launch (dt_set_option "pdl") on one planner pass (local map + cond + K = 1 sampler +
+"""A/B of a launch option -- programmatic dependent launch (dt_set_option "pdl", default) or EXP_OPT=fork -- on one planner pass (local map + cond + K = 1 sampler +
 8-step propagate) at small batches: device time per pass, bit-identity of the actions, and the sampler call alone
 through its CUDA-graph replay (B <= 64)."""
 import os, sys, time
@@ -17,8 +17,9 @@ enc, unet = denoiser_flops(1, down_dims=dims)
 batches = [int(b) for b in os.environ.get("SB_BATCHES", "1,16,64,256,1024,4096").split(",")]
 reps = int(os.environ.get("SB_REPS", "30"))
 ref = {}
+OPT = os.environ.get("EXP_OPT", "pdl")   # "pdl" or "fork" (side stream for the residual 1 x 1 convs)
 for pdl in (0, 1, 0, 1):
-    ctx.set_option("pdl", pdl)
+    ctx.set_option(OPT, pdl)
     for B in batches:
         st, prev = synth_candidates(grid, B, 1)
         st = torch.as_tensor(st).cuda(); prev = torch.as_tensor(prev).cuda()
@@ -42,5 +43,5 @@ for pdl in (0, 1, 0, 1):
         e1.record(); t_host = (time.perf_counter() - t0) / reps * 1e3
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"pdl={pdl} B={B:5d}: device {ms:7.3f} ms / pass, host enqueue {t_host:6.3f} ms, "
+        print(f"{OPT}={pdl} B={B:5d}: device {ms:7.3f} ms / pass, host enqueue {t_host:6.3f} ms, "
               f"{B*(enc+unet)/ms/1e9:7.1f} TFLOP/s, actions identical to the first run: {same}", flush=True)

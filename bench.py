@@ -608,6 +608,40 @@ def main():
                     "to whole 32-byte sectors (1216 B for 1200 B of data; the padding is NOT counted as achieved "
                     "bytes); inputs (419 MB) and trajectory (1.26 GB) exceed the 126 MB L2"}
 
+    del stp, actp
+    # ---------------- the other geometry kernels against the HBM roofline ----------------
+    geometry = None
+    if world == 1 and not args.no_configs:
+        def timed(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(reps):
+                fn()
+            g1.record()
+            torch.cuda.synchronize()
+            return g0.elapsed_time(g1) / reps
+        rng_g = np.random.default_rng(0)
+        Ng, Pg = 1 << 24, 1 << 20
+        xyz = torch.as_tensor(np.stack([rng_g.uniform(-10, 10, Ng), rng_g.uniform(-10, 10, Ng), rng_g.uniform(-3.2, 3.2, Ng)],
+                                       1).astype(np.float32)).cuda()
+        geometry = {}
+        for name, fn, units, bytes_unit in (
+                ("collide_car", lambda: ctx.collide_car(xyz), Ng, 13),
+                ("local_map_f32", lambda: ctx.local_map(xyz[:Pg], 20, 0.2), Pg, 12 + 400 * 4),
+                ("local_map_bf16_signed", lambda: ctx.local_map(xyz[:Pg], 20, 0.2, bf16_signed=True), Pg, 12 + 400 * 2)):
+            ms_g = timed(fn)
+            geometry[name] = {"units": units, "ms": ms_g, "units_per_s": units / ms_g * 1e3, "bytes_per_unit": bytes_unit,
+                              "achieved": units * bytes_unit / ms_g / 1e6, "peak": hbm, "unit": "GB/s",
+                              "frac": units * bytes_unit / ms_g / 1e6 / hbm, "bound": "hbm"}
+        geometry["note"] = ("is_colliding_car on 2^24 (x, y, theta) rows (12 B in + 1 B flag out each: 201 + 16 MB per launch); "
+                            "create_local_map on 2^20 poses, 20 x 20 points (fp32 {0,1}: 1.7 GB out per launch; bf16 2m-1 as the "
+                            "encoder reads it: 0.84 GB) -- all beyond the 126 MB L2; issue-bound kernels measured against the "
+                            "HBM bound their algorithmic bytes would allow")
+        del xyz
+
     configs = None
     if world == 1 and not args.no_configs:
         try:
@@ -628,7 +662,7 @@ def main():
                            "D2H side returns what propagate_action_sequence_env returns: final states, flags, the "
                            "executed actions and the (B, S, 6) state sequences"},
             "gpu_launches": int(launches), "collision_free_edges_last_step": ok_edges, "parity_check": parity,
-            "roofline": roofline, "roofline_propagate": prop, "cpu_baseline": cb, "suite": suite, "configs": configs,
+            "roofline": roofline, "roofline_propagate": prop, "roofline_geometry": geometry, "cpu_baseline": cb, "suite": suite, "configs": configs,
             "clocks": clocks.summary()}
     emit(line)
     if world > 1:

@@ -51,7 +51,12 @@ const char* dt_version(void);
  * hundred candidates) split K over all SMs and reduce in a second kernel -- ~2x less latency, but a
  * candidate's bits then depend on whether it was sampled alone or in a batch (different fp32 summation order,
  * same 2e-2 tolerance).  0 restores batch-size independent results.  Changing the value synchronises the
- * device and drops the captured sampler graphs (they bake in the kernel selection). */
+ * device and drops the captured sampler graphs (they bake in the kernel selection).
+ * "pdl" (default 1; env DITREE_PDL=0): the denoiser's kernels are launched with programmatic stream serialization --
+ * a kernel's CTAs are scheduled and run their prologue while the previous kernel drains, griddepcontrol.wait orders
+ * the memory traffic.  "fork" (default 1; env DITREE_FORK=0): at sampler batches <= 128 the 1 x 1 residual convs of
+ * the U-Net and the downsample branches of the encoder run on a side stream beside the block's first conv.  Neither
+ * changes a single bit of the results (same kernels, same arithmetic, different overlap). */
 int dt_set_option(dt_ctx* ctx, const char* name, int value);
 
 /* Occupancy grid upload.  Replaces RRT_Planner.update_maze / BasePlanner.maze

@@ -166,6 +166,31 @@ def test_local_map_other_sizes(ctx, mazes, n_side):
     assert np.array_equal(signed, want.astype(np.float32) * 2 - 1)
 
 
+@pytest.mark.parametrize("n_side,scale,sg", [(20, 0.2, 1.0), (16, 0.8, 4.0)])
+def test_local_map_quad_border_poses(ctx, mazes, n_side, scale, sg):
+    """The quad kernel (N = 16 / 20) on poses that put whole rows of lattice points ON cell borders (axis-aligned headings,
+    positions on the lattice pitch): every such point is inside the fp32 guard band, so the per-block list of deferred
+    float64 decisions overflows and the in-line fallback runs too; plus far-outside and non-finite poses (every point
+    exact).  Bit-exact against the oracle, both output types, unaligned tail of the batch included."""
+    grid = mazes["random_large"] if sg == 1.0 else mazes["random_huge"]
+    ctx.set_map(grid, sg)
+    R, C = grid.shape
+    rng = np.random.default_rng(n_side)
+    n = 20_003
+    k = rng.integers(-int(C * sg / scale / 2), int(C * sg / scale / 2), (n, 2))
+    pose = np.stack([k[:, 0] * (scale / 2), k[:, 1] * (scale / 2), rng.integers(-4, 5, n) * (np.pi / 2)], 1)
+    pose[::7, 2] += rng.uniform(-1e-6, 1e-6, len(pose[::7]))          # a hair off the axis
+    pose[5::101, :2] = rng.uniform(-3 * C * sg, 3 * C * sg, (len(pose[5::101]), 2))   # centres far outside the map
+    pose[11::503, 2] = 1.0e5                                           # heading beyond the MUFU range
+    pose = pose.astype(np.float32)
+    p64 = pose.astype(np.float64)
+    want = orc.local_map(grid, p64[:, 0], p64[:, 1], p64[:, 2], n_side, scale, sg, (C * sg / 2, R * sg / 2))
+    got = ctx.local_map(dev(pose), n_side, scale).cpu().numpy()
+    assert np.array_equal(got, want)
+    signed = ctx.local_map(dev(pose), n_side, scale, bf16_signed=True).float().cpu().numpy()
+    assert np.array_equal(signed, want.astype(np.float32) * 2 - 1)
+
+
 # ---- dynamics ------------------------------------------------------------------------------
 def rel_err(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)

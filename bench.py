@@ -357,6 +357,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    t_start = time.perf_counter()
+
+    def note(msg):
+        # progress marks on stderr (every rank): a multi-rank run that stalls shows WHERE in its log
+        print(f"[bench rank {rank}/{world} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    if world > 1:
+        # Multi-rank runs keep the launch configuration every multi-GPU measurement of this repository was taken with:
+        # programmatic dependent launch and the side-stream forks (dt_set_option "pdl" / "fork": +1 % on this workload,
+        # validated on one GPU) stay off unless asked for explicitly.
+        os.environ.setdefault("DITREE_PDL", "0")
+        os.environ.setdefault("DITREE_FORK", "0")
     from ditreeonlineplanner_b200.data import load_maze, load_metadata
     grid = load_maze(args.maze).astype(np.float32)
     meta = load_metadata("carmaze")
@@ -380,7 +392,13 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        note("init_process_group(nccl) ...")
+        import datetime
+        # no collective of this benchmark legitimately waits minutes (the longest wait is for rank 0's ~40 s parity
+        # check): a stalled peer makes the watchdog abort the job instead of hanging it
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=300))
+        note("process group up")
     from ditreeonlineplanner_b200 import get_context
     from ditreeonlineplanner_b200.expansion import TreeExpander
     from ditreeonlineplanner_b200.policies.fm_policy import DiffusionSampler
@@ -416,9 +434,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("weights packed; warm-up steps ...")
     for _ in range(max(3, args.warmup)):
         res = exp.expand_device(st, prev, goal, noise=noise)
     barrier()
+    note("timed steps ...")
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = ctx.launches
@@ -444,6 +464,7 @@ def main():
     ok_edges = int((res["first_coll"] < 0).sum().item())
     parity = parity_check(args, grid, meta, sd, st_np, prev_np, noise, res) if rank == 0 else None
 
+    note("device-timed steps done; e2e leg ...")
     # ---------------- e2e through the host-facing API ----------------
     for _ in range(2):
         exp.expand(st_np, prev_np, goal, want_traj=True)
@@ -460,6 +481,7 @@ def main():
 
     # ---------------- scenario suite, (scenario, run)-sharded over the ranks ----------------
     suite = None
+    note("e2e done; suite leg ...")
     if not args.no_suite:
         from ditreeonlineplanner_b200 import scenarios as sc
         from ditreeonlineplanner_b200.common.map_utils import invalidate_staged_map
@@ -475,6 +497,7 @@ def main():
         reps = []
         for rep in range(args.suite_repeats):
             barrier()
+            note(f"suite repeat {rep} ...")
             t0 = time.perf_counter()
             table, _ = sc.run_suite(sampler, total_runs=suite_runs, time_budget=1e9, rank=rank, world=world,
                                     device=ctx.device, planner_kwargs=suite_kw, engine="device")
@@ -522,6 +545,7 @@ def main():
         ctx.set_map(grid)
         invalidate_staged_map()
 
+    note("suite done; gathering")
     # per-rank results gathered over NCCL (the only collective of this path: result rows)
     if world > 1:
         mine = torch.tensor([float(ok_edges), float(B)], device="cuda")

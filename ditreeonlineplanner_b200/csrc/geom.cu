@@ -925,11 +925,12 @@ static int local_map_fast_launch_t(dt_ctx* ctx, const MapView& m, const float* x
   const bool quad_ok = (N == 20 || N == 16) && (reinterpret_cast<uintptr_t>(out) & (sizeof(OutT) == 4 ? 15u : 7u)) == 0 &&
                        (!kMulti || (mm.group_size % 16 == 0 && B % 16 == 0));
   if (quad_ok) {
-    static bool qattr_done = false;
-    if (!qattr_done) {
+    static unsigned long long qattr_done = 0;   // one bit per device: the attribute is per device (and per instantiation)
+    const unsigned long long qdev_bit = 1ull << (ctx->device & 63);
+    if (!(qattr_done & qdev_bit)) {
       DT_CUDA(cudaFuncSetAttribute(k_local_map_quad<OutT, kMulti, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       DT_CUDA(cudaFuncSetAttribute(k_local_map_quad<OutT, kMulti, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      qattr_done = true;
+      qattr_done |= qdev_bit;
     }
     // two poses per warp; a single wave of resident blocks (LM_MINB per SM) strides over the poses: a second,
     // partial wave would leave most SMs with one block
@@ -941,12 +942,13 @@ static int local_map_fast_launch_t(dt_ctx* ctx, const MapView& m, const float* x
     return DT_OK;
   }
   const int it = (N * N + 63) / 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+  if (!(attr_done & dev_bit)) {
     DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     DT_CUDA(cudaFuncSetAttribute(k_local_map_fast<OutT, kMulti, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done = true;
+    attr_done |= dev_bit;
   }
   if (it <= 4) k_local_map_fast<OutT, kMulti, 4><<<blocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, N, ax, out, mm);
   else if (it <= 7) k_local_map_fast<OutT, kMulti, 7><<<blocks, GEOM_THREADS, smem, st>>>(m, x, y, theta, stride, B, N, ax, out, mm);

@@ -68,8 +68,15 @@ def test_sass_opcodes_are_blackwell_native():
     for k, c in gemm.items():
         assert c["UTCHMMA"] >= 4 and c["LDTM"] >= 2 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 2, (k, dict(c))
         assert c["STL"] == 0 and c["LDL"] == 0, (k, "register spills in the GEMM kernel")
+        # programmatic dependent launch: griddepcontrol.launch_dependents / .wait (SASS PREEXIT / ACQBULK)
+        assert c["PREEXIT"] >= 1 and c["ACQBULK"] >= 1, (k, dict(c))
     assert sum(1 for c in gemm.values() if c["UTCHMMA.2CTA"] >= 4) >= len(gemm) // 2
     assert all(c["HMMA"] == 0 for c in per.values())
+    # every kernel of the denoiser chain that is launched with the programmatic attribute waits before its first access
+    for name in ("k_splitk_epi", "k_prep_sample", "k_final_euler", "k_film_input", "k_time_mlp1", "k_time_mlp2", "k_film_time",
+                 "k_im2col", "k_maxpool3s2", "k_avgpool", "k_copy_cols"):
+        hit = [c for k, c in per.items() if name in k]
+        assert hit and all(c["ACQBULK"] >= 1 for c in hit), name
     for name in ("k_propagate_rows", "k_collide_car4", "k_local_map", "k_lidar_scan"):
         hit = [c for k, c in per.items() if name in k]
         assert hit and all(c["UBLKCP"] >= 1 for c in hit), name

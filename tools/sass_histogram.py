@@ -15,7 +15,8 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "ditreeonlineplanner_b200", "libditree.so")
-WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "MUFU", "HMMA", "STL", "LDL"]
+WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "PREEXIT", "ACQBULK", "MUFU", "HMMA", "STL",
+         "LDL"]
 
 
 def demangle(names):
@@ -61,7 +62,8 @@ def main():
              "`cuobjdump -sass ditreeonlineplanner_b200/libditree.so`, counted by `tools/sass_histogram.py`. "
              "`UTCHMMA` = tcgen05.mma.kind::f16 (`.2CTA` = cta_group::2), `LDTM` = tcgen05.ld, `UTMALDG` = "
              "cp.async.bulk.tensor (TMA tile loads), `UBLKCP` = cp.async.bulk (1-D TMA: the occupancy grid), `UTCBAR` = "
-             "tcgen05.commit, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async, `MUFU` = SFU (sin/cos/ex2/rcp), `STL`/`LDL` = "
+             "tcgen05.commit, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async, `PREEXIT` / `ACQBULK` = griddepcontrol.launch_dependents / "
+             ".wait (programmatic dependent launch), `MUFU` = SFU (sin/cos/ex2/rcp), `STL`/`LDL` = "
              "local-memory spills. No `HMMA` (mma.sync) anywhere.", "",
              "| kernel | instr | " + " | ".join(cols) + " |", "|---|---|" + "---|" * len(cols)]
     for k, c in per.items():
